@@ -1,0 +1,126 @@
+// b200_dev.cuh -- device-visible state of a connection and the integer helpers
+// shared by the sm_100a kernels and the host runtime.
+//
+// Reference being replaced (paths relative to the reference root):
+//   RingBufferPollable state      src/core/lib/ibverbs/ring_buffer.h:203-208
+//   PairPollable cursors/credit   src/core/lib/ibverbs/pair.h:100-103,168-172
+//   credit / framing arithmetic   src/core/lib/ibverbs/ring_buffer.h:180-189,
+//                                 ring_buffer.cc:99-116
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B200_HD __host__ __device__ __forceinline__
+#else
+#define B200_HD inline
+#endif
+
+namespace b200 {
+
+constexpr uint64_t kAlign = 8;          // ring_buffer.h:49
+constexpr uint64_t kReserved = 24;      // ring_buffer.h:52 (header, footer, one spare word)
+constexpr uint64_t kFooter = ~0ull;     // ring_buffer.h:50
+constexpr int kMaxSgeLimit = 32;        // planner handles one warp of slices per Send call
+
+B200_HD uint64_t round_up8(uint64_t v) { return (v + 7) & ~7ull; }
+B200_HD uint64_t round_down8(uint64_t v) { return v & ~7ull; }
+// GetEncodedSize, ring_buffer.h:180-183
+B200_HD uint64_t encoded_size(uint64_t payload) { return 16 + round_up8(payload); }
+// CalculateWritableSize, ring_buffer.h:185-189
+B200_HD uint64_t calc_writable(uint64_t space) { return space > kReserved ? round_down8(space - kReserved) : 0; }
+// GetFreeSize, ring_buffer.cc:99-104
+B200_HD uint64_t free_size(uint64_t cap, uint64_t head, uint64_t tail) {
+  return cap - ((tail + cap - head) & (cap - 1));
+}
+// GetWritableSize(head, tail), ring_buffer.cc:106-116
+B200_HD uint64_t writable_size(uint64_t cap, uint64_t head, uint64_t tail) {
+  uint64_t f = free_size(cap, head, tail);
+  return f > kReserved ? f - kReserved : 0;
+}
+
+// Host-visible mirror of one pair (pinned, GPU-mapped).  Kernels refresh it at
+// the end of every op that touches the pair so that HasMessage /
+// HasPendingWrites / get_status stay wait-free host reads (pair.cc:288-303).
+struct PairMirror {
+  uint64_t head, moving_head, remain, acc;
+  uint64_t remote_tail, credit_head;
+  uint64_t readable;       // GetReadableSize() as of the last refresh
+  uint32_t partial_write;  // HasPendingWrites()
+  uint32_t peer_exit;      // status_report.peer_exit seen by this pair
+  uint32_t has_message;    // HasMessage()
+  uint32_t seq;            // bumped on every refresh
+};
+
+// One connection endpoint in HBM.  Three blocks with distinct writers:
+//   setup  : written by the host at Init/Connect/Disconnect only
+//   cursor : owned by this pair's own send/recv kernels
+//   credit : the 16-byte status_report the PEER writes (pair.h:100-103);
+//            16-byte aligned so one v2.u64 store updates it atomically
+struct __align__(128) PairDev {
+  // ---- setup
+  uint8_t* ring;         // this pair's receive ring (HBM), all-zero when empty
+  uint64_t cap;          // power of two (ring_buffer.cc:22)
+  uint8_t* peer_ring;    // where Send lands frames: the peer's ring (remote_addr)
+  uint64_t* peer_credit; // address of the peer's credit block
+  PairMirror* mirror;
+  PairMirror* peer_mirror;  // loopback wire only, else nullptr
+  uint32_t status;       // b200_status as the host last set it
+  uint32_t max_sge;      // frames per Send call (pair.cc:672)
+  int32_t peer_slot;     // loopback wire: index of the peer in this table, else -1
+  uint32_t wire;         // 0 = same device, 1 = peer device over NVLink (system-scope fences)
+  // ---- cursor
+  uint64_t head;         // RingBufferPollable::head_
+  uint64_t moving_head;  // moving_head_
+  uint64_t remain;       // remain_
+  uint64_t acc;          // PairPollable::internal_read_size_
+  uint64_t remote_tail;  // PairPollable::remote_tail_
+  uint32_t partial_write;
+  uint32_t _pad0;
+  // ---- credit (offset 112, 16-byte aligned)
+  uint64_t credit_head;  // status_report.remote_head
+  uint32_t credit_exit;  // status_report.peer_exit
+  uint32_t _pad1;
+};
+static_assert(sizeof(PairDev) == 128, "PairDev is one 128-byte line");
+
+struct SliceDev {  // same layout as b200_slice
+  const uint8_t* ptr;
+  uint64_t len;
+};
+
+struct SendOpDev {
+  int32_t slot;
+  uint32_t flags;  // B200_BATCH_*
+  const SliceDev* slices;
+  uint64_t nslices;
+  uint64_t byte_idx;
+};
+
+struct RecvOpDev {
+  int32_t slot;
+  uint32_t flags;
+  uint8_t* dst;
+  uint64_t cap;
+};
+
+// per-op result: bytes moved and number of Send/Recv calls that moved > 0
+struct OpResult {
+  uint64_t bytes;
+  uint64_t calls;
+};
+
+constexpr uint32_t kFlagUntilBlocked = 0x1;
+constexpr uint32_t kEvReadable = 0x1;
+constexpr uint32_t kEvWritable = 0x4;
+
+constexpr uint32_t kStConnected = 2;
+constexpr uint32_t kStHalfClosed = 3;
+constexpr uint32_t kStError = 5;
+
+// launch wrappers (b200_kernels.cu)
+void launch_send(PairDev* pairs, const SendOpDev* ops, OpResult* results, int nops, void* stream);
+void launch_recv(PairDev* pairs, const RecvOpDev* ops, OpResult* results, int nops, void* stream);
+void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, uint32_t* ready_count,
+                      int32_t* ready_slots, int n, void* stream);
+
+}  // namespace b200

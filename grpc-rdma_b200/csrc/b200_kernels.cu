@@ -1,0 +1,628 @@
+// b200_kernels.cu -- sm_100a kernels of the RDMA_BPEV endpoint hot path.
+//
+//   k_send       gather/encode: grpc_slice list -> [len][payload][pad][~0] frames
+//                written straight at the remote tail of the peer's HBM ring
+//                (replaces PairPollable::Send pair.cc:645-734 + AppendHeader/
+//                Payload/Footer ring_buffer.h:84-99 + GetWriteRequests
+//                ring_buffer.cc:261-330 + the NIC's RDMA write)
+//   k_recv       deframe/scatter + clear-on-read + credit write-back (replaces
+//                RingBufferPollable::Read ring_buffer.cc:122-191 and
+//                PairPollable::Recv/updateStatus pair.cc:264-286,624-641)
+//   k_poll_scan  readiness scan (replaces the per-pair body of
+//                Poller::begin_polling poller.cc:66-101 and of the engine's
+//                busy-poll window ev_epollex_rdma_bpev_linux.cc:1104-1145)
+//
+// Pure indexing / memcpy work: HBM-bound, no tensor cores.  All bulk traffic is
+// 16-byte vector loads/stores; byte granularity only at the <16-byte edges of
+// a copy.  One CTA serves one (pair, op); inside the CTA, warp 0 does the
+// per-call integer planning with warp scans and all warps move bytes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200_dev.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------ memory helpers
+
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+// ring reads must not use the non-coherent path: the ring is written by other
+// kernels / the wire while we run
+__device__ __forceinline__ uint4 ld_ring16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream16(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_u64(const void* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_v2u64(void* p, uint64_t a, uint64_t b) {
+  // 16-byte status_report {remote_head, peer_exit}: fence + one vector store
+  __threadfence_system();
+  asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+// Take bytes [m, m+16) out of the 32-byte concatenation A|B (m = 1..15).
+template <bool kHi, bool kShift>
+__device__ __forceinline__ uint4 shift_window(uint4 A, uint4 B, unsigned sh) {
+  uint64_t a0 = (uint64_t)A.x | ((uint64_t)A.y << 32), a1 = (uint64_t)A.z | ((uint64_t)A.w << 32);
+  uint64_t b0 = (uint64_t)B.x | ((uint64_t)B.y << 32), b1 = (uint64_t)B.z | ((uint64_t)B.w << 32);
+  uint64_t w0 = kHi ? a1 : a0, w1 = kHi ? b0 : a1, w2 = kHi ? b1 : b0;
+  uint64_t lo, hi;
+  if (kShift) {
+    lo = (w0 >> sh) | (w1 << (64 - sh));
+    hi = (w1 >> sh) | (w2 << (64 - sh));
+  } else {
+    lo = w0;
+    hi = w1;
+  }
+  uint4 r;
+  r.x = (uint32_t)lo;
+  r.y = (uint32_t)(lo >> 32);
+  r.z = (uint32_t)hi;
+  r.w = (uint32_t)(hi >> 32);
+  return r;
+}
+
+template <bool kRingSrc>
+__device__ __forceinline__ uint4 ld_src16(const void* p) {
+  return kRingSrc ? ld_ring16(p) : ld_stream16(p);
+}
+
+constexpr int kUnroll = 4;
+
+// dst 16-byte aligned, src misaligned by m = src & 15 (1..15): every output
+// vector is cut out of two aligned source vectors.  The second one always
+// contains a byte of the source range, so it never faults.
+template <bool kRingSrc, bool kHi, bool kShift>
+__device__ __noinline__ void copy_vec_shifted(uint8_t* dst, const uint8_t* src_al, uint64_t nvec, unsigned sh,
+                                              uint32_t tid, uint32_t nthr) {
+  const uint4* s = reinterpret_cast<const uint4*>(src_al);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint64_t step = (uint64_t)nthr * kUnroll;
+  const uint64_t nfull = nvec / step * step;  // whole blocks: no predicates, kUnroll loads in flight
+  uint64_t base = tid;
+  for (; base < nfull; base += step) {
+    uint4 A[kUnroll], B[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++) {
+      A[k] = ld_src16<kRingSrc>(s + base + (uint64_t)k * nthr);
+      B[k] = ld_src16<kRingSrc>(s + base + (uint64_t)k * nthr + 1);
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++)
+      st_stream16(d + base + (uint64_t)k * nthr, shift_window<kHi, kShift>(A[k], B[k], sh));
+  }
+  for (uint64_t i = nfull + tid; i < nvec; i += nthr) {
+    uint4 A = ld_src16<kRingSrc>(s + i), B = ld_src16<kRingSrc>(s + i + 1);
+    st_stream16(d + i, shift_window<kHi, kShift>(A, B, sh));
+  }
+}
+
+template <bool kRingSrc>
+__device__ __noinline__ void copy_vec_aligned(uint8_t* dst, const uint8_t* src, uint64_t nvec, uint32_t tid,
+                                              uint32_t nthr) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint64_t step = (uint64_t)nthr * kUnroll;
+  const uint64_t nfull = nvec / step * step;
+  uint64_t base = tid;
+  for (; base < nfull; base += step) {
+    uint4 v[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++) v[k] = ld_src16<kRingSrc>(s + base + (uint64_t)k * nthr);
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++) st_stream16(d + base + (uint64_t)k * nthr, v[k]);
+  }
+  for (uint64_t i = nfull + tid; i < nvec; i += nthr) st_stream16(d + i, ld_src16<kRingSrc>(s + i));
+}
+
+// Cooperative copy of n bytes, any alignment on either side, by threads
+// tid in [0, nthr).  Bulk = aligned 16-byte stores; <16-byte head and tail use
+// one byte per thread.
+template <bool kRingSrc>
+__device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint64_t n, uint32_t tid,
+                                          uint32_t nthr) {
+  if (n == 0) return;
+  uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+  if (head > n) head = n;
+  if (tid < head) dst[tid] = kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(src + tid) : src[tid];
+  dst += head;
+  src += head;
+  n -= head;
+  uint64_t nvec = n >> 4;
+  unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15);
+  if (nvec) {
+    if (m == 0) {
+      copy_vec_aligned<kRingSrc>(dst, src, nvec, tid, nthr);
+    } else {
+      const uint8_t* sal = src - m;
+      unsigned sh = (m & 7) * 8;
+      if (m & 8) {
+        if (sh) copy_vec_shifted<kRingSrc, true, true>(dst, sal, nvec, sh, tid, nthr);
+        else copy_vec_shifted<kRingSrc, true, false>(dst, sal, nvec, sh, tid, nthr);
+      } else {
+        copy_vec_shifted<kRingSrc, false, true>(dst, sal, nvec, sh, tid, nthr);
+      }
+    }
+  }
+  uint64_t done = nvec << 4;
+  uint64_t tail = n - done;
+  if (tid < tail)
+    dst[done + tid] = kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(src + done + tid) : src[done + tid];
+}
+
+// Cooperative zero fill of n bytes at p (any alignment).
+__device__ __forceinline__ void coop_zero(uint8_t* p, uint64_t n, uint32_t tid, uint32_t nthr) {
+  if (n == 0) return;
+  uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+  if (head > n) head = n;
+  if (tid < head) p[tid] = 0;
+  p += head;
+  n -= head;
+  uint64_t nvec = n >> 4;
+  uint4* d = reinterpret_cast<uint4*>(p);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (uint64_t i = tid; i < nvec; i += nthr) st_stream16(d + i, z);
+  uint64_t done = nvec << 4;
+  if (tid < n - done) p[done + tid] = 0;
+}
+
+// GetReadableSize / HasMessage of a pair whose cursor is (head, remain)
+// (ring_buffer.cc:56-97).  A header larger than cap-24 is a torn read in the
+// reference (it spins); here it reports "not readable yet".
+__device__ __forceinline__ void rx_probe(const uint8_t* ring, uint64_t cap, uint64_t head, uint64_t remain,
+                                         uint32_t& has_msg, uint64_t& readable) {
+  if (remain > 0) {
+    has_msg = 1;
+    readable = remain;
+    return;
+  }
+  uint64_t hdr = ld_acquire_u64(ring + head);
+  has_msg = hdr != 0;
+  readable = 0;
+  if (hdr != 0 && hdr <= cap - kReserved) {
+    uint64_t foot = ld_acquire_u64(ring + ((head + 8 + round_up8(hdr)) & (cap - 1)));
+    if (foot == kFooter) readable = hdr;
+  }
+}
+
+__device__ __forceinline__ void publish_mirror(PairMirror* m, const PairDev* P, uint32_t has_msg,
+                                               uint64_t readable) {
+  if (m == nullptr) return;
+  volatile PairMirror* vm = m;
+  vm->head = P->head;
+  vm->moving_head = P->moving_head;
+  vm->remain = P->remain;
+  vm->acc = P->acc;
+  vm->remote_tail = P->remote_tail;
+  vm->credit_head = P->credit_head;
+  vm->readable = readable;
+  vm->partial_write = P->partial_write;
+  vm->peer_exit = P->credit_exit;
+  vm->has_message = has_msg;
+  __threadfence_system();
+  vm->seq = vm->seq + 1;
+}
+
+// =========================================================================
+// k_send
+// =========================================================================
+
+constexpr int kSendThreads = 256;
+constexpr uint64_t kChunk = 16384;  // bytes of payload one warp moves per work item
+
+struct FrameDesc {
+  const uint8_t* src;
+  uint64_t len;   // payload bytes
+  uint64_t off;   // ring offset of the frame header
+  uint32_t first_item;  // prefix of work items
+  uint32_t _pad;
+};
+
+struct SendShared {
+  uint64_t rt, rh, cap, staging, total_left, written_total, ncalls;
+  uint64_t cur, bidx;
+  uint32_t nframes, nitems, stop, partial, status, max_sge;
+  FrameDesc frames[kMaxSgeLimit];
+};
+
+__global__ void __launch_bounds__(kSendThreads, 3)
+k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult* __restrict__ results) {
+  __shared__ SendShared S;
+  __shared__ unsigned long long s_total;
+  const SendOpDev op = ops[blockIdx.x];
+  PairDev* P = &pairs[op.slot];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nwarps = kSendThreads / 32;
+
+  if (tid == 0) {
+    s_total = 0;
+    S.rt = P->remote_tail;
+    S.cap = P->cap;
+    S.staging = P->cap / 2;  // send_buf_size = recv_buf_size / 2, pair.cc:104
+    S.status = P->status;
+    S.max_sge = P->max_sge;
+    S.cur = 0;
+    S.bidx = op.byte_idx;
+    S.written_total = 0;
+    S.ncalls = 0;
+    S.partial = P->partial_write;
+    S.stop = 0;
+  }
+  __syncthreads();
+  // total_slice_size, pair.cc:661-664
+  {
+    unsigned long long part = 0;
+    for (uint64_t i = tid; i < op.nslices; i += kSendThreads) part += op.slices[i].len;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if (lane == 0 && part) atomicAdd(&s_total, part);
+  }
+  __syncthreads();
+  if (tid == 0) S.total_left = s_total - op.byte_idx;
+  __syncthreads();
+
+  if (S.status != kStConnected) {  // pair.cc:657
+    if (tid == 0) {
+      results[blockIdx.x].bytes = 0;
+      results[blockIdx.x].calls = 0;
+    }
+    return;
+  }
+  const uint64_t mask = S.cap - 1;
+  uint8_t* ring = P->peer_ring;
+  const bool sys_scope = P->wire != 0;
+
+  while (true) {
+    // ------------------------------------------------ plan one Send() call
+    if (warp == 0) {
+      const uint64_t cap = S.cap, rt = S.rt;
+      // credit snapshot, once per call (pair.cc:650)
+      const uint64_t rh = ld_acquire_u64(&P->credit_head);
+      const uint64_t cur = S.cur, bidx = S.bidx;
+      const uint64_t idx = cur + lane;
+      bool valid = lane < S.max_sge && idx < op.nslices;
+      const uint8_t* ptr = nullptr;
+      uint64_t len = 0;
+      if (valid) {
+        SliceDev sl = op.slices[idx];
+        uint64_t skip = lane == 0 ? bidx : 0;
+        ptr = sl.ptr + skip;
+        len = sl.len - skip;
+      }
+      uint64_t e = valid ? encoded_size(len) : 0;
+      uint64_t incl = e;  // inclusive scan of encoded sizes
+      for (int o = 1; o < 32; o <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint64_t a = incl - e;  // bytes of staging / ring consumed before this slice
+      // min(CWS(send_buf_free), CWS(recv_buf_free)): both shrink by `a`
+      const uint64_t fr = free_size(cap, rh, rt);
+      const uint64_t lim = S.staging < fr ? S.staging : fr;
+      const uint64_t room = calc_writable(lim > a ? lim - a : 0);
+      const bool fits = valid && len != 0 && len <= room;
+      const unsigned bad = __ballot_sync(0xffffffffu, !fits);  // invalid lanes count as bad
+      const int first_bad = __ffs(bad) - 1;                    // lane 31 valid+fits => bad==0 => -1
+      const int nfull = first_bad < 0 ? 32 : first_bad;
+      uint64_t p = 0;
+      if ((int)lane < nfull) p = len;
+      else if ((int)lane == nfull && valid && len != 0) p = room;  // cut: space ran out (pair.cc:676-681)
+      const unsigned fmask = __ballot_sync(0xffffffffu, p != 0);
+      const uint32_t nframes = __popc(fmask);
+      uint64_t wsum = p, esum = p ? encoded_size(p) : 0;
+      uint32_t items = p ? (uint32_t)((p + kChunk - 1) / kChunk) : 0;
+      uint32_t items_incl = items;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, items_incl, o);
+        if (lane >= o) items_incl += t;
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        esum += __shfl_xor_sync(0xffffffffu, esum, o);
+      }
+      if (p) {
+        FrameDesc& f = S.frames[lane];  // frames are lanes 0..nframes-1 (contiguous)
+        f.src = ptr;
+        f.len = p;
+        f.off = (rt + a) & mask;
+        f.first_item = items_incl - items;
+      }
+      const uint32_t nitems = __shfl_sync(0xffffffffu, items_incl, 31);
+      // cursor advance (rdma_flush, rdma_bp_posix.cc:480-493)
+      const uint64_t cut_p = __shfl_sync(0xffffffffu, p, nfull < 32 ? nfull : 0);
+      if (lane == 0) {
+        S.nframes = nframes;
+        S.nitems = nitems;
+        S.rt = (rt + esum) & mask;
+        S.partial = wsum < S.total_left;  // pair.cc:712
+        S.total_left -= wsum;
+        S.written_total += wsum;
+        if (wsum) S.ncalls++;
+        uint64_t ncur = cur + nfull, nb = 0;
+        if (nfull < 32 && nframes > (uint32_t)nfull) {  // the cut slice stays current
+          nb = (nfull == 0 ? bidx : 0) + cut_p;
+        } else if (nfull == 0) {
+          nb = bidx;  // nothing consumed
+        }
+        S.cur = ncur;
+        S.bidx = nb;
+        S.stop = (wsum == 0) || !(op.flags & kFlagUntilBlocked) || S.total_left == 0;
+      }
+    }
+    __syncthreads();
+    const uint32_t nframes = S.nframes, nitems = S.nitems;
+    // ------------------------------------------------ move the bytes
+    for (uint32_t w = warp; w < nitems; w += nwarps) {
+      uint32_t f = 0;
+      while (f + 1 < nframes && S.frames[f + 1].first_item <= w) f++;
+      const FrameDesc fd = S.frames[f];
+      const uint64_t c0 = (uint64_t)(w - fd.first_item) * kChunk;
+      uint64_t n = fd.len - c0;
+      if (n > kChunk) n = kChunk;
+      if (c0 == 0 && lane == 0) *reinterpret_cast<uint64_t*>(ring + fd.off) = fd.len;  // AppendHeader
+      uint64_t pos = (fd.off + 8 + c0) & mask;
+      uint64_t seg1 = S.cap - pos;
+      if (seg1 > n) seg1 = n;
+      coop_copy<false>(ring + pos, fd.src + c0, seg1, lane, 32);
+      if (n > seg1) coop_copy<false>(ring, fd.src + c0 + seg1, n - seg1, lane, 32);  // wrap: WR1 at remote+0
+    }
+    // footer last: a frame is complete for the reader only when header != 0 and
+    // footer == ~0 (ring_buffer.cc:75-96), so everything else must be visible first
+    if (sys_scope) __threadfence_system();
+    else __threadfence();
+    __syncthreads();
+    if (tid < nframes) {
+      const FrameDesc fd = S.frames[tid];
+      *reinterpret_cast<uint64_t*>(ring + ((fd.off + 8 + round_up8(fd.len)) & mask)) = kFooter;
+    }
+    const bool stop = S.stop;
+    __syncthreads();
+    if (stop) break;
+  }
+
+  if (tid == 0) {
+    P->remote_tail = S.rt;
+    P->partial_write = S.partial;
+    results[blockIdx.x].bytes = S.written_total;
+    results[blockIdx.x].calls = S.ncalls;
+    publish_mirror(P->mirror, P, P->mirror ? ((volatile PairMirror*)P->mirror)->has_message : 0,
+                   P->mirror ? ((volatile PairMirror*)P->mirror)->readable : 0);
+    // loopback wire: the peer lives in this table, refresh its readiness hint
+    if (P->peer_slot >= 0 && S.written_total) {
+      __threadfence();
+      PairDev* Q = &pairs[P->peer_slot];
+      uint32_t hm;
+      uint64_t rd;
+      rx_probe(Q->ring, Q->cap, *(volatile uint64_t*)&Q->head, *(volatile uint64_t*)&Q->remain, hm, rd);
+      if (Q->mirror) {
+        volatile PairMirror* vm = Q->mirror;
+        vm->has_message = hm;
+        vm->readable = rd;
+        __threadfence_system();
+        vm->seq = vm->seq + 1;
+      }
+    }
+  }
+}
+
+// =========================================================================
+// k_recv
+// =========================================================================
+
+constexpr int kRecvThreads = 256;
+
+struct RecvShared {
+  uint64_t head, mh, remain, acc, cap;
+  uint64_t delivered, cap_left, ncalls;
+  // current call
+  uint64_t n, src_off, zstart, zlen, credit_val;
+  uint32_t credit_flag, stop, status;
+};
+
+__global__ void __launch_bounds__(kRecvThreads, 3)
+k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult* __restrict__ results) {
+  __shared__ RecvShared S;
+  const RecvOpDev op = ops[blockIdx.x];
+  PairDev* P = &pairs[op.slot];
+  const uint32_t tid = threadIdx.x;
+
+  if (tid == 0) {
+    S.head = P->head;
+    S.mh = P->moving_head;
+    S.remain = P->remain;
+    S.acc = P->acc;
+    S.cap = P->cap;
+    S.status = P->status;
+    S.delivered = 0;
+    S.cap_left = op.cap;
+    S.ncalls = 0;
+  }
+  __syncthreads();
+  if (S.status != kStConnected) {  // pair.cc:266-268
+    if (tid == 0) {
+      results[blockIdx.x].bytes = 0;
+      results[blockIdx.x].calls = 0;
+    }
+    return;
+  }
+  uint8_t* ring = P->ring;
+  const uint64_t cap = S.cap, mask = cap - 1;
+
+  while (true) {
+    // ------------------------------------------------ one Recv() call: plan
+    if (tid == 0) {
+      uint64_t r = 0;
+      bool opening = false;
+      if (S.remain > 0) {
+        r = S.remain;
+      } else {  // GetReadableSize, ring_buffer.cc:67-97
+        uint32_t hm;
+        rx_probe(ring, cap, S.head, 0, hm, r);
+        opening = r > 0;
+      }
+      uint64_t n = r < S.cap_left ? r : S.cap_left;
+      S.n = n;
+      S.credit_flag = 0;
+      if (n > 0) {
+        const uint64_t prev_mh = S.mh;
+        if (opening) {  // first touch of this frame, ring_buffer.cc:135-147
+          S.mh = (S.head + 8) & mask;
+          S.head = (S.head + 16 + round_up8(r)) & mask;
+        }
+        S.src_off = S.mh;
+        S.zstart = prev_mh;  // between frames moving_head == head: covers the header word too
+        S.mh = (S.mh + n) & mask;
+        S.remain = r - n;
+        if (S.remain == 0) {  // pad + footer, ring_buffer.cc:170-183
+          S.mh = round_up8(S.mh) & mask;
+          S.mh = (S.mh + 8) & mask;
+        }
+        const uint64_t internal = (S.mh + cap - prev_mh) & mask;
+        S.zlen = internal;  // everything retired this call gets cleared
+        S.acc += internal;
+        if (S.acc >= cap / 2) {  // pair.cc:276-284
+          S.credit_flag = 1;
+          S.credit_val = S.mh;
+          S.acc = 0;
+        }
+        S.ncalls++;
+      }
+      S.stop = (n == 0) || !(op.flags & kFlagUntilBlocked) || (S.cap_left - n == 0);
+    }
+    __syncthreads();
+    const uint64_t n = S.n;
+    if (n == 0) break;
+    // ------------------------------------------------ scatter payload
+    {
+      uint8_t* dst = op.dst + S.delivered;
+      const uint64_t pos = S.src_off;
+      uint64_t seg1 = cap - pos;
+      if (seg1 > n) seg1 = n;
+      coop_copy<true>(dst, ring + pos, seg1, tid, kRecvThreads);
+      if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, tid, kRecvThreads);
+    }
+    __syncthreads();  // every load of this call is done before anything is cleared
+    // ------------------------------------------------ clear-on-read
+    {
+      const uint64_t z0 = S.zstart, zl = S.zlen;
+      uint64_t seg1 = cap - z0;
+      if (seg1 > zl) seg1 = zl;
+      coop_zero(ring + z0, seg1, tid, kRecvThreads);
+      if (zl > seg1) coop_zero(ring, zl - seg1, tid, kRecvThreads);
+    }
+    const bool credit = S.credit_flag != 0;
+    if (credit) {  // the sender may reuse the space only once it reads as zero
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        // updateStatus, pair.cc:624-641: 16-byte status_report to the peer
+        st_release_v2u64(P->peer_credit, S.credit_val, 0);
+        if (P->peer_mirror) ((volatile PairMirror*)P->peer_mirror)->credit_head = S.credit_val;
+      }
+    }
+    const bool stop = S.stop;
+    __syncthreads();
+    if (tid == 0) {
+      S.delivered += n;
+      S.cap_left -= n;
+    }
+    if (stop) break;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    P->head = S.head;
+    P->moving_head = S.mh;
+    P->remain = S.remain;
+    P->acc = S.acc;
+    results[blockIdx.x].bytes = S.delivered;
+    results[blockIdx.x].calls = S.ncalls;
+    uint32_t hm;
+    uint64_t rd;
+    rx_probe(ring, cap, S.head, S.remain, hm, rd);
+    publish_mirror(P->mirror, P, hm, rd);
+  }
+}
+
+// =========================================================================
+// k_poll_scan
+// =========================================================================
+
+__global__ void __launch_bounds__(128)
+k_poll_scan(PairDev* __restrict__ pairs, const int32_t* __restrict__ slots, uint32_t* __restrict__ events,
+            uint32_t* __restrict__ ready_count, int32_t* __restrict__ ready_slots, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t ev = 0;
+  int32_t slot = -1;
+  if (i < n) {
+    slot = slots[i];
+    PairDev* P = &pairs[slot];
+    const uint32_t st = *(volatile uint32_t*)&P->status;
+    if (st == kStConnected) {
+      const uint32_t exit_flag = ld_acquire_u32(&P->credit_exit);
+      uint32_t hm;
+      uint64_t rd;
+      rx_probe(P->ring, P->cap, *(volatile uint64_t*)&P->head, *(volatile uint64_t*)&P->remain, hm, rd);
+      const uint32_t pw = *(volatile uint32_t*)&P->partial_write;
+      if (exit_flag == 1) {
+        ev = kEvReadable;  // HalfClosed: force a read event (engine :1130-1137)
+      } else {
+        if (hm) ev |= kEvReadable;
+        if (pw) ev |= kEvWritable;
+      }
+      publish_mirror(P->mirror, P, hm, rd);
+    } else if (st == kStError || st == kStHalfClosed) {
+      ev = kEvReadable;
+    }
+    events[i] = ev;
+  }
+  // warp-aggregated append to the ready set
+  const unsigned m = __ballot_sync(0xffffffffu, ev != 0);
+  if (m) {
+    uint32_t base = 0;
+    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(ready_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (ev) ready_slots[base + __popc(m & ((1u << lane) - 1))] = slot;
+  }
+}
+
+// ---------------------------------------------------------------- launchers
+
+void launch_send(PairDev* pairs, const SendOpDev* ops, OpResult* results, int nops, void* stream) {
+  if (nops <= 0) return;
+  k_send<<<nops, kSendThreads, 0, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
+}
+void launch_recv(PairDev* pairs, const RecvOpDev* ops, OpResult* results, int nops, void* stream) {
+  if (nops <= 0) return;
+  k_recv<<<nops, kRecvThreads, 0, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
+}
+void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, uint32_t* ready_count,
+                      int32_t* ready_slots, int n, void* stream) {
+  if (n <= 0) return;
+  k_poll_scan<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(pairs, slots, events, ready_count,
+                                                                               ready_slots, n);
+}
+
+}  // namespace b200

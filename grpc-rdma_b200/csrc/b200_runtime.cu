@@ -1,0 +1,937 @@
+// b200_runtime.cu -- host runtime behind include/b200_pair.h.
+//
+// Owns the HBM-resident connection table (PairDev[]), the pinned host mirrors,
+// the pair pool, the bootstrap blob / loopback wire registry, the single-call
+// and batched submit paths and the background poller.  No data byte is touched
+// by the CPU on the batch path; the single-pair calls bounce UNREGISTERED host
+// memory through pinned staging exactly like the reference copies slices into
+// its registered send buffer (pair.cc:690-694).
+//
+// Reference counterparts (relative to the reference root):
+//   PairPollable lifecycle  src/core/lib/ibverbs/pair.cc:85-168,325-375
+//   PairPool                src/core/lib/ibverbs/pair.h:273-333
+//   Poller                  src/core/lib/ibverbs/poller.cc:12-106
+//   Config                  src/core/lib/ibverbs/config.cc:45-115
+//   Address blob            src/core/lib/ibverbs/address.h:24-31
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <poll.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/eventfd.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/b200_pair.h"
+#include "b200_dev.cuh"
+
+using namespace b200;
+
+// ----------------------------------------------------------------- errors
+
+static thread_local std::string t_err;
+static void set_err(const std::string& s) { t_err = s; }
+#define CU_OK(call)                                                                      \
+  ([&]() -> bool {                                                                       \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      set_err(std::string(#call) + ": " + cudaGetErrorString(e__));                      \
+      return false;                                                                      \
+    }                                                                                    \
+    return true;                                                                         \
+  }())
+
+// ------------------------------------------------------------------ config
+
+struct Config {
+  uint64_t ring_bytes = 4096ull * 1024;  // GRPC_RDMA_RING_BUFFER_SIZE_KB, config.cc:90-96
+  int poller_threads = 1;                // GRPC_RDMA_POLLER_THREAD_NUM, config.cc:66-73
+  int busy_poll_us = 500;                // GRPC_RDMA_BUSY_POLLING_TIMEOUT_US, config.cc:75-81
+  int poller_sleep_ms = 1000;            // GRPC_RDMA_POLLER_SLEEP_TIMEOUT_MS, config.cc:83-89
+  int max_sge = 30;                      // ibv_device_attr.max_sge on the authors' HCA
+};
+
+// Address blob: same 48-byte layout as grpc_core::ibverbs::Address::addr_
+struct AddrBlob {
+  uint32_t lid;
+  uint32_t qpn;
+  uint32_t psn;
+  uint32_t _pad0;
+  uint8_t gid[16];
+  uint32_t tag;
+  uint32_t _pad1;
+  uint64_t ring_buffer_size;
+};
+static_assert(sizeof(AddrBlob) == B200_ADDRESS_BYTES, "address blob must stay 48 bytes");
+
+struct b200_pair {
+  int slot = -1;
+  int status = B200_UNINITIALIZED;
+  std::string id, error;
+  uint8_t* ring = nullptr;
+  uint64_t cap = 0;
+  int wakeup_fd = -1;
+  PairMirror* mirror = nullptr;
+  AddrBlob self{};
+  AddrBlob peer{};
+  b200_pair* peer_local = nullptr;  // loopback wire
+  bool in_poller = false;
+};
+
+struct b200_batch {
+  int kind = 0;  // 0 send, 1 recv
+  int nops = 0;
+  int flags = 0;
+  void* d_ops = nullptr;       // SendOpDev[] / RecvOpDev[]
+  SliceDev* d_slices = nullptr;
+  OpResult* d_results = nullptr;
+  OpResult* h_results = nullptr;  // pinned
+};
+
+namespace {
+
+constexpr int kMaxPairs = 8192;
+
+struct Runtime {
+  std::mutex mu;       // setup + single-call submit
+  bool inited = false;
+  int dev = -1;
+  Config cfg;
+  cudaStream_t stream = nullptr;       // single-call + setup stream
+  cudaStream_t poll_stream = nullptr;  // readiness scans
+  PairDev* d_pairs = nullptr;
+  PairMirror* h_mirrors = nullptr;  // pinned, mapped
+  std::vector<b200_pair*> all_pairs;
+  std::queue<b200_pair*> pool;
+  std::vector<int> free_slots;
+  std::unordered_map<std::string, b200_pair*> id_pair;
+  std::map<uint32_t, b200_pair*> by_qpn;  // loopback wire registry
+  uint32_t next_qpn = 0x200;
+  uint32_t cookie = 0;
+  // single-call staging (pinned, GPU-mapped)
+  SendOpDev* h_sop = nullptr;
+  RecvOpDev* h_rop = nullptr;
+  SliceDev* h_slices = nullptr;  // kMaxSgeLimit + 1 entries
+  OpResult* h_res = nullptr;
+  uint8_t* bounce_tx = nullptr;
+  uint8_t* bounce_rx = nullptr;
+  uint64_t bounce_tx_cap = 0, bounce_rx_cap = 0;
+  std::atomic<uint64_t> launches{0};
+  // poller
+  std::mutex pmu;
+  std::condition_variable pcv;
+  std::vector<b200_pair*> pollables;
+  std::vector<std::thread> poll_threads;
+  std::atomic<bool> poll_running{false};
+  // scan scratch (pinned)
+  int32_t* h_scan_slots = nullptr;
+  uint32_t* h_scan_events = nullptr;
+  uint32_t* h_scan_count = nullptr;
+  int32_t* h_scan_ready = nullptr;
+  std::mutex scan_mu;
+};
+
+Runtime& R() {
+  static Runtime r;
+  return r;
+}
+
+bool ensure_init() {
+  if (R().inited) return true;
+  return b200_init(-1) == 0;
+}
+
+long env_long(const char* k, long dflt) {
+  const char* v = getenv(k);
+  return v ? atol(v) : dflt;
+}
+
+bool is_pow2(uint64_t v) { return v && (v & (v - 1)) == 0; }
+
+bool write_setup(Runtime& r, b200_pair* p, const PairDev& hd) {
+  // setup block = first 64 bytes of PairDev
+  return CU_OK(cudaMemcpyAsync(&r.d_pairs[p->slot], &hd, 64, cudaMemcpyHostToDevice, r.stream)) &&
+         CU_OK(cudaStreamSynchronize(r.stream));
+}
+
+// what kind of memory is this? 0 = unregistered host, 1 = GPU-addressable
+int mem_kind(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return a.type == cudaMemoryTypeUnregistered ? 0 : 1;
+}
+
+void kick(b200_pair* p) {
+  if (p->wakeup_fd >= 0) (void)eventfd_write(p->wakeup_fd, 1);
+}
+
+}  // namespace
+
+// =================================================================== runtime
+
+extern "C" int b200_init(int device) {
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (r.inited) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_err("b200_init: no CUDA device (this library has no CPU fallback)");
+    return -1;
+  }
+  if (device < 0) {
+    const char* e = getenv("B200_DEVICE");
+    if (e) device = atoi(e);
+    else if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (!CU_OK(cudaSetDevice(device))) return -1;
+  cudaDeviceProp prop;
+  if (!CU_OK(cudaGetDeviceProperties(&prop, device))) return -1;
+  if (prop.major < 10) {
+    set_err("b200_init: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+            ", this library is built for sm_100a only");
+    return -1;
+  }
+  r.dev = device;
+  // environment, same keys as the reference (config.cc:45-115)
+  r.cfg.ring_bytes = (uint64_t)env_long("GRPC_RDMA_RING_BUFFER_SIZE_KB", 4096) * 1024;
+  if (getenv("B200_RING_BUFFER_SIZE_BYTES")) r.cfg.ring_bytes = (uint64_t)env_long("B200_RING_BUFFER_SIZE_BYTES", 0);
+  r.cfg.poller_threads = (int)env_long("GRPC_RDMA_POLLER_THREAD_NUM", 1);
+  r.cfg.busy_poll_us = (int)env_long("GRPC_RDMA_BUSY_POLLING_TIMEOUT_US", 500);
+  r.cfg.poller_sleep_ms = (int)env_long("GRPC_RDMA_POLLER_SLEEP_TIMEOUT_MS", 1000);
+  r.cfg.max_sge = (int)env_long("GRPC_RDMA_MAX_SGE", 30);
+  if (r.cfg.max_sge < 1 || r.cfg.max_sge > kMaxSgeLimit) r.cfg.max_sge = 30;
+
+  if (!CU_OK(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking))) return -1;
+  if (!CU_OK(cudaStreamCreateWithFlags(&r.poll_stream, cudaStreamNonBlocking))) return -1;
+  if (!CU_OK(cudaMalloc(&r.d_pairs, sizeof(PairDev) * kMaxPairs))) return -1;
+  if (!CU_OK(cudaMemset(r.d_pairs, 0, sizeof(PairDev) * kMaxPairs))) return -1;
+  if (!CU_OK(cudaHostAlloc(&r.h_mirrors, sizeof(PairMirror) * kMaxPairs, cudaHostAllocMapped | cudaHostAllocPortable)))
+    return -1;
+  memset(r.h_mirrors, 0, sizeof(PairMirror) * kMaxPairs);
+  auto halloc = [&](void** p, size_t n) {
+    return CU_OK(cudaHostAlloc(p, n, cudaHostAllocMapped | cudaHostAllocPortable));
+  };
+  if (!halloc((void**)&r.h_sop, sizeof(SendOpDev)) || !halloc((void**)&r.h_rop, sizeof(RecvOpDev)) ||
+      !halloc((void**)&r.h_slices, sizeof(SliceDev) * (kMaxSgeLimit + 1)) ||
+      !halloc((void**)&r.h_res, sizeof(OpResult)) ||
+      !halloc((void**)&r.h_scan_slots, sizeof(int32_t) * kMaxPairs) ||
+      !halloc((void**)&r.h_scan_events, sizeof(uint32_t) * kMaxPairs) ||
+      !halloc((void**)&r.h_scan_count, sizeof(uint32_t) * 4) ||
+      !halloc((void**)&r.h_scan_ready, sizeof(int32_t) * kMaxPairs))
+    return -1;
+  r.free_slots.clear();
+  for (int i = kMaxPairs - 1; i >= 0; i--) r.free_slots.push_back(i);
+  r.cookie = (uint32_t)getpid() * 2654435761u ^ (uint32_t)(uintptr_t)&r;
+  static bool at_exit_registered = false;
+  if (!at_exit_registered) {
+    at_exit_registered = true;
+    atexit(b200_poller_shutdown);  // poller threads must be joined before static destruction
+  }
+  r.inited = true;
+  return 0;
+}
+
+extern "C" void b200_shutdown(void) {
+  b200_poller_shutdown();
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (!r.inited) return;
+  cudaSetDevice(r.dev);
+  cudaDeviceSynchronize();
+  for (b200_pair* p : r.all_pairs) {
+    if (p->ring) cudaFree(p->ring);
+    if (p->wakeup_fd >= 0) close(p->wakeup_fd);
+    delete p;
+  }
+  r.all_pairs.clear();
+  while (!r.pool.empty()) r.pool.pop();
+  r.id_pair.clear();
+  r.by_qpn.clear();
+  cudaFree(r.d_pairs);
+  cudaFreeHost(r.h_mirrors);
+  cudaFreeHost(r.h_sop);
+  cudaFreeHost(r.h_rop);
+  cudaFreeHost(r.h_slices);
+  cudaFreeHost(r.h_res);
+  cudaFreeHost(r.h_scan_slots);
+  cudaFreeHost(r.h_scan_events);
+  cudaFreeHost(r.h_scan_count);
+  cudaFreeHost(r.h_scan_ready);
+  if (r.bounce_tx) cudaFreeHost(r.bounce_tx);
+  if (r.bounce_rx) cudaFreeHost(r.bounce_rx);
+  r.bounce_tx = r.bounce_rx = nullptr;
+  r.bounce_tx_cap = r.bounce_rx_cap = 0;
+  cudaStreamDestroy(r.stream);
+  cudaStreamDestroy(r.poll_stream);
+  r.inited = false;
+}
+
+extern "C" int b200_device(void) { return R().dev; }
+extern "C" const char* b200_last_error(void) { return t_err.c_str(); }
+extern "C" uint64_t b200_launch_count(void) { return R().launches.load(); }
+
+extern "C" int b200_config_set(const char* key, const char* value) {
+  if (!ensure_init()) return -1;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  std::string k(key);
+  long v = atol(value);
+  if (k == "GRPC_RDMA_RING_BUFFER_SIZE_KB") {
+    if (v <= 0) return -1;
+    r.cfg.ring_bytes = (uint64_t)v * 1024;
+  } else if (k == "B200_RING_BUFFER_SIZE_BYTES") {
+    if (v <= (long)kReserved) return -1;
+    r.cfg.ring_bytes = (uint64_t)v;
+  } else if (k == "GRPC_RDMA_POLLER_THREAD_NUM") {
+    if (v <= 0) return -1;
+    r.cfg.poller_threads = (int)v;
+  } else if (k == "GRPC_RDMA_BUSY_POLLING_TIMEOUT_US") {
+    if (v < 0) return -1;
+    r.cfg.busy_poll_us = (int)v;
+  } else if (k == "GRPC_RDMA_POLLER_SLEEP_TIMEOUT_MS") {
+    if (v < 0) return -1;
+    r.cfg.poller_sleep_ms = (int)v;
+  } else if (k == "GRPC_RDMA_MAX_SGE") {
+    if (v < 1 || v > kMaxSgeLimit) return -1;
+    r.cfg.max_sge = (int)v;
+  } else {
+    set_err("b200_config_set: unknown key " + k);
+    return -1;
+  }
+  return 0;
+}
+
+extern "C" int64_t b200_config_get(const char* key) {
+  if (!ensure_init()) return -1;
+  Runtime& r = R();
+  std::string k(key);
+  if (k == "GRPC_RDMA_RING_BUFFER_SIZE_KB") return (int64_t)(r.cfg.ring_bytes / 1024);
+  if (k == "B200_RING_BUFFER_SIZE_BYTES") return (int64_t)r.cfg.ring_bytes;
+  if (k == "GRPC_RDMA_POLLER_THREAD_NUM") return r.cfg.poller_threads;
+  if (k == "GRPC_RDMA_BUSY_POLLING_TIMEOUT_US") return r.cfg.busy_poll_us;
+  if (k == "GRPC_RDMA_POLLER_SLEEP_TIMEOUT_MS") return r.cfg.poller_sleep_ms;
+  if (k == "GRPC_RDMA_MAX_SGE") return r.cfg.max_sge;
+  return -1;
+}
+
+// ==================================================================== memory
+
+extern "C" void* b200_mem_alloc_device(size_t bytes) {
+  if (!ensure_init()) return nullptr;
+  void* p = nullptr;
+  cudaSetDevice(R().dev);
+  if (!CU_OK(cudaMalloc(&p, bytes ? bytes : 1))) return nullptr;
+  return p;
+}
+extern "C" void b200_mem_free_device(void* p) {
+  if (p) cudaFree(p);
+}
+extern "C" void* b200_mem_alloc_host(size_t bytes) {
+  if (!ensure_init()) return nullptr;
+  void* p = nullptr;
+  cudaSetDevice(R().dev);
+  if (!CU_OK(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable))) return nullptr;
+  return p;
+}
+extern "C" void b200_mem_free_host(void* p) {
+  if (p) cudaFreeHost(p);
+}
+extern "C" int b200_mem_register_host(void* p, size_t bytes) {
+  if (!ensure_init()) return -1;
+  return CU_OK(cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable)) ? 0 : -1;
+}
+extern "C" int b200_mem_unregister_host(void* p) { return CU_OK(cudaHostUnregister(p)) ? 0 : -1; }
+extern "C" int b200_memcpy(void* dst, const void* src, size_t bytes, int dir, void* stream) {
+  if (!ensure_init()) return -1;
+  cudaMemcpyKind k = dir == 0 ? cudaMemcpyHostToDevice : dir == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  cudaStream_t s = stream ? (cudaStream_t)stream : R().stream;
+  return CU_OK(cudaMemcpyAsync(dst, src, bytes, k, s)) ? 0 : -1;
+}
+extern "C" int b200_stream_sync(void* stream) {
+  if (!ensure_init()) return -1;
+  cudaStream_t s = stream ? (cudaStream_t)stream : R().stream;
+  return CU_OK(cudaStreamSynchronize(s)) ? 0 : -1;
+}
+
+// ================================================================ pool / pair
+
+extern "C" b200_pair* b200_pool_take(const char* id) {
+  if (!ensure_init()) return nullptr;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  b200_pair* p = nullptr;
+  if (!r.pool.empty()) {
+    p = r.pool.front();
+    r.pool.pop();
+  } else {
+    if (r.free_slots.empty()) {
+      set_err("b200_pool_take: connection table full");
+      return nullptr;
+    }
+    p = new b200_pair();
+    p->slot = r.free_slots.back();
+    r.free_slots.pop_back();
+    p->mirror = &r.h_mirrors[p->slot];
+    p->wakeup_fd = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);  // grpc_wakeup_fd_init, pair.cc:74
+    r.all_pairs.push_back(p);
+  }
+  p->id = id ? id : "";
+  if (!p->id.empty()) r.id_pair[p->id] = p;
+  return p;
+}
+
+extern "C" void b200_pool_putback(b200_pair* p) {
+  if (!p) return;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  auto it = r.id_pair.find(p->id);
+  if (it != r.id_pair.end() && it->second == p) r.id_pair.erase(it);
+  r.pool.push(p);
+}
+
+extern "C" b200_pair* b200_pool_get(const char* id) {
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  auto it = r.id_pair.find(id ? id : "");
+  return it == r.id_pair.end() ? nullptr : it->second;
+}
+
+extern "C" void b200_pair_init(b200_pair* p) {
+  if (!p || !ensure_init()) return;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  // pair.cc:88-89: only from Uninitialized / Error / Disconnected
+  if (!(p->status == B200_UNINITIALIZED || p->status == B200_ERROR || p->status == B200_DISCONNECTED)) return;
+  cudaSetDevice(r.dev);
+  const uint64_t cap = r.cfg.ring_bytes;
+  if (!is_pow2(cap) || cap <= kReserved) {  // ring_buffer.cc:22-23
+    p->error = "ring buffer size must be a power of two > 24";
+    set_err(p->error);
+    p->status = B200_ERROR;
+    return;
+  }
+  if (p->ring && p->cap != cap) {
+    cudaFree(p->ring);
+    p->ring = nullptr;
+  }
+  if (!p->ring) {
+    if (!CU_OK(cudaMalloc(&p->ring, cap))) {
+      p->error = t_err;
+      p->status = B200_ERROR;
+      return;
+    }
+  }
+  p->cap = cap;
+  PairDev hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.ring = p->ring;
+  hd.cap = cap;
+  hd.mirror = p->mirror;
+  hd.status = B200_INITIALIZED;
+  hd.max_sge = (uint32_t)r.cfg.max_sge;
+  hd.peer_slot = -1;
+  memset(p->mirror, 0, sizeof(PairMirror));
+  bool ok = CU_OK(cudaMemsetAsync(p->ring, 0, cap, r.stream)) &&  // RingBufferPollable::Init
+            CU_OK(cudaMemcpyAsync(&r.d_pairs[p->slot], &hd, sizeof(hd), cudaMemcpyHostToDevice, r.stream)) &&
+            CU_OK(cudaStreamSynchronize(r.stream));
+  if (!ok) {
+    p->error = t_err;
+    p->status = B200_ERROR;
+    return;
+  }
+  // drop a stale registration, then publish the new address
+  if (p->self.qpn) r.by_qpn.erase(p->self.qpn);
+  memset(&p->self, 0, sizeof(p->self));
+  p->self.lid = 0xB200;
+  p->self.qpn = r.next_qpn++;
+  p->self.psn = (uint32_t)rand() & 0xffffff;
+  memcpy(p->self.gid, &r.cookie, 4);           // which process
+  memcpy(p->self.gid + 4, &r.dev, 4);          // which GPU
+  memcpy(p->self.gid + 8, &p->slot, 4);        // which row of the connection table
+  p->self.tag = B200_PAIR_TAG_POLLABLE;
+  p->self.ring_buffer_size = cap;  // "used to check peer has the same size", pair.cc:107
+  r.by_qpn[p->self.qpn] = p;
+  p->peer_local = nullptr;
+  p->error.clear();
+  eventfd_t junk;
+  (void)eventfd_read(p->wakeup_fd, &junk);
+  p->status = B200_INITIALIZED;
+}
+
+extern "C" size_t b200_pair_self_address(b200_pair* p, void* out48) {
+  if (!p || !out48) return 0;
+  memcpy(out48, &p->self, sizeof(AddrBlob));
+  return sizeof(AddrBlob);
+}
+
+extern "C" int b200_pair_connect(b200_pair* p, const void* peer48, size_t n) {
+  if (!p || !ensure_init()) return 0;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (p->status != B200_INITIALIZED) return 0;  // pair.cc:144
+  if (n != sizeof(AddrBlob)) {                  // address.cc:13 asserts
+    p->error = "peer address blob has the wrong size";
+    set_err(p->error);
+    return 0;
+  }
+  memcpy(&p->peer, peer48, sizeof(AddrBlob));
+  if (p->peer.tag != p->self.tag) {  // pair.cc:148 (GPR_ASSERT there)
+    p->error = "peer pair tag mismatch";
+    set_err(p->error);
+    return 0;
+  }
+  if (p->peer.ring_buffer_size != p->self.ring_buffer_size) {  // pair.cc:149
+    p->error = "peer ring buffer size mismatch";
+    set_err(p->error);
+    return 0;
+  }
+  uint32_t cookie;
+  memcpy(&cookie, p->peer.gid, 4);
+  auto it = r.by_qpn.find(p->peer.qpn);
+  if (cookie != r.cookie || it == r.by_qpn.end() || it->second->self.psn != p->peer.psn) {
+    p->error = "peer is not reachable: only the in-process loopback wire is built (no NIC / IPC wire)";
+    set_err(p->error);
+    return 0;
+  }
+  b200_pair* q = it->second;
+  if (!q->ring) {
+    p->error = "peer ring not allocated";
+    set_err(p->error);
+    return 0;
+  }
+  cudaSetDevice(r.dev);
+  PairDev hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.ring = p->ring;
+  hd.cap = p->cap;
+  hd.peer_ring = q->ring;
+  hd.peer_credit = &r.d_pairs[q->slot].credit_head;
+  hd.mirror = p->mirror;
+  hd.peer_mirror = q->mirror;
+  hd.status = B200_CONNECTED;
+  hd.max_sge = (uint32_t)r.cfg.max_sge;
+  hd.peer_slot = q->slot;
+  hd.wire = 0;
+  if (!write_setup(r, p, hd)) {
+    p->error = t_err;
+    p->status = B200_ERROR;
+    return 0;
+  }
+  p->peer_local = q;
+  p->status = B200_CONNECTED;
+  return 1;
+}
+
+extern "C" void b200_pair_disconnect(b200_pair* p) {
+  if (!p || !R().inited) return;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (p->status == B200_UNINITIALIZED || p->status == B200_DISCONNECTED) return;  // pair.cc:326-327
+  cudaSetDevice(r.dev);
+  const bool was_connected = p->status == B200_CONNECTED && p->mirror->peer_exit == 0;
+  if (was_connected && p->peer_local) {
+    // peer_exit = 1 + current head, one 16-byte status write (pair.cc:330-337)
+    cudaStreamSynchronize(r.stream);
+    struct {
+      uint64_t remote_head;
+      uint32_t peer_exit, pad;
+    } st = {p->mirror->moving_head, 1, 0};
+    b200_pair* q = p->peer_local;
+    cudaMemcpyAsync(&r.d_pairs[q->slot].credit_head, &st, 16, cudaMemcpyHostToDevice, r.stream);
+    cudaStreamSynchronize(r.stream);
+    q->mirror->credit_head = st.remote_head;
+    q->mirror->peer_exit = 1;
+  }
+  uint32_t st = B200_DISCONNECTED;
+  cudaMemcpyAsync(&r.d_pairs[p->slot].status, &st, 4, cudaMemcpyHostToDevice, r.stream);
+  cudaStreamSynchronize(r.stream);
+  if (p->self.qpn) r.by_qpn.erase(p->self.qpn);
+  p->self.qpn = 0;
+  p->peer_local = nullptr;
+  p->status = B200_DISCONNECTED;
+}
+
+extern "C" enum b200_status b200_pair_status(b200_pair* p) {
+  if (!p) return B200_UNINITIALIZED;
+  if (p->status == B200_CONNECTED && ((volatile PairMirror*)p->mirror)->peer_exit == 1)
+    return B200_HALF_CLOSED;  // pair.cc:354-356
+  return (enum b200_status)p->status;
+}
+extern "C" const char* b200_pair_error(const b200_pair* p) { return p ? p->error.c_str() : ""; }
+extern "C" int b200_pair_wakeup_read_fd(b200_pair* p) { return p ? p->wakeup_fd : -1; }
+extern "C" void b200_pair_consume_wakeup(b200_pair* p) {
+  if (!p) return;
+  eventfd_t v;
+  (void)eventfd_read(p->wakeup_fd, &v);
+}
+extern "C" int b200_pair_has_message(const b200_pair* p) {
+  return p && ((volatile PairMirror*)p->mirror)->has_message != 0;
+}
+extern "C" int b200_pair_has_pending_writes(const b200_pair* p) {
+  return p && ((volatile PairMirror*)p->mirror)->partial_write != 0;
+}
+extern "C" uint64_t b200_pair_readable(const b200_pair* p) {
+  if (!p || p->status != B200_CONNECTED) return 0;  // pair.cc:290-292
+  return ((volatile PairMirror*)p->mirror)->readable;
+}
+extern "C" uint64_t b200_pair_writable(const b200_pair* p) {
+  if (!p || !p->cap) return 0;
+  volatile PairMirror* m = p->mirror;
+  return writable_size(p->cap, m->credit_head, m->remote_tail);  // pair.cc:294-301
+}
+
+extern "C" int b200_pair_get_state(b200_pair* p, b200_pair_state* out) {
+  if (!p || !out || !ensure_init()) return -1;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  cudaSetDevice(r.dev);
+  PairDev hd;
+  if (!CU_OK(cudaMemcpy(&hd, &r.d_pairs[p->slot], sizeof(hd), cudaMemcpyDeviceToHost))) return -1;
+  out->head = hd.head;
+  out->moving_head = hd.moving_head;
+  out->remain = hd.remain;
+  out->remote_tail = hd.remote_tail;
+  out->internal_read_size = hd.acc;
+  out->credit_remote_head = hd.credit_head;
+  out->partial_write = hd.partial_write;
+  out->peer_exit = hd.credit_exit;
+  out->ring_capacity = hd.cap;
+  return 0;
+}
+
+extern "C" int b200_pair_copy_ring(b200_pair* p, void* host_dst, uint64_t cap) {
+  if (!p || !p->ring || cap < p->cap) return -1;
+  cudaSetDevice(R().dev);
+  return CU_OK(cudaMemcpy(host_dst, p->ring, p->cap, cudaMemcpyDeviceToHost)) ? 0 : -1;
+}
+
+// ================================================================ single call
+
+static bool ensure_bounce(uint8_t** buf, uint64_t* cap, uint64_t need) {
+  if (*cap >= need) return true;
+  if (*buf) cudaFreeHost(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  if (!CU_OK(cudaHostAlloc((void**)buf, need, cudaHostAllocMapped | cudaHostAllocPortable))) return false;
+  *cap = need;
+  return true;
+}
+
+extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
+  if (!p || !ensure_init()) return 0;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (p->status != B200_CONNECTED || n == 0) return 0;
+  // The peer told us it left (peer_exit): its ring may already belong to a new
+  // connection, so nothing is written; rdma_flush then reports "Peer has been
+  // exited" from get_status() exactly as with the reference (rdma_bp_posix.cc:507-511).
+  if (((volatile PairMirror*)p->mirror)->peer_exit == 1) return 0;
+  cudaSetDevice(r.dev);
+  // One Send call looks at <= max_sge slices; the rest only contributes to
+  // total_slice_size (pair.cc:661-664), folded into one trailing pseudo-slice
+  // that is never dereferenced.
+  const size_t look = n < (size_t)r.cfg.max_sge ? n : (size_t)r.cfg.max_sge;
+  uint64_t rest = 0;
+  for (size_t i = look; i < n; i++) rest += slices[i].len;
+  uint64_t bounce_off = 0;
+  for (size_t i = 0; i < look; i++) {
+    const uint8_t* ptr = (const uint8_t*)slices[i].ptr;
+    uint64_t len = slices[i].len;
+    if (len && mem_kind(ptr) == 0) {
+      // unregistered host memory: stage like the reference's send buffer
+      const uint64_t skip = i == 0 ? byte_idx : 0;
+      const uint64_t useful = len - skip;
+      const uint64_t limit = p->cap / 2;  // a call never accepts more than the staging size
+      uint64_t take = useful < limit ? useful : limit;
+      if (!ensure_bounce(&r.bounce_tx, &r.bounce_tx_cap, p->cap + 16 * (kMaxSgeLimit + 4))) return 0;
+      if (bounce_off + take > r.bounce_tx_cap) take = r.bounce_tx_cap - bounce_off;
+      memcpy(r.bounce_tx + bounce_off, ptr + skip, take);
+      // keep (ptr + skip) pointing at the staged bytes
+      r.h_slices[i].ptr = r.bounce_tx + bounce_off - skip;
+      bounce_off += (take + 15) & ~15ull;
+    } else {
+      r.h_slices[i].ptr = ptr;
+    }
+    r.h_slices[i].len = len;
+  }
+  size_t nsl = look;
+  if (rest) {
+    r.h_slices[nsl].ptr = nullptr;
+    r.h_slices[nsl].len = rest;
+    nsl++;
+  }
+  r.h_sop->slot = p->slot;
+  r.h_sop->flags = B200_BATCH_ONE_CALL;
+  r.h_sop->slices = r.h_slices;
+  r.h_sop->nslices = nsl;
+  r.h_sop->byte_idx = byte_idx;
+  r.h_res->bytes = 0;
+  r.h_res->calls = 0;
+  launch_send(r.d_pairs, r.h_sop, r.h_res, 1, r.stream);
+  r.launches++;
+  if (!CU_OK(cudaGetLastError()) || !CU_OK(cudaStreamSynchronize(r.stream))) {
+    p->error = t_err;
+    p->status = B200_ERROR;
+    return 0;
+  }
+  return r.h_res->bytes;
+}
+
+extern "C" uint64_t b200_pair_recv(b200_pair* p, void* dst, uint64_t cap) {
+  if (!p || !ensure_init()) return 0;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (p->status != B200_CONNECTED || cap == 0) return 0;
+  cudaSetDevice(r.dev);
+  const bool bounce = mem_kind(dst) == 0;
+  uint8_t* kdst = (uint8_t*)dst;
+  uint64_t kcap = cap;
+  if (bounce) {
+    if (kcap > p->cap) kcap = p->cap;  // one frame never exceeds the ring
+    if (!ensure_bounce(&r.bounce_rx, &r.bounce_rx_cap, p->cap)) return 0;
+    kdst = r.bounce_rx;
+  }
+  r.h_rop->slot = p->slot;
+  r.h_rop->flags = B200_BATCH_ONE_CALL;
+  r.h_rop->dst = kdst;
+  r.h_rop->cap = kcap;
+  r.h_res->bytes = 0;
+  r.h_res->calls = 0;
+  launch_recv(r.d_pairs, r.h_rop, r.h_res, 1, r.stream);
+  r.launches++;
+  if (!CU_OK(cudaGetLastError()) || !CU_OK(cudaStreamSynchronize(r.stream))) {
+    p->error = t_err;
+    p->status = B200_ERROR;
+    return 0;
+  }
+  const uint64_t got = r.h_res->bytes;
+  if (bounce && got) memcpy(dst, r.bounce_rx, got);
+  return got;
+}
+
+// ===================================================================== batch
+
+static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int flags) {
+  if (!ensure_init()) return nullptr;
+  Runtime& r = R();
+  cudaSetDevice(r.dev);
+  b200_batch* b = new b200_batch();
+  b->kind = kind;
+  b->nops = (int)nops;
+  b->flags = flags;
+  bool ok = true;
+  if (kind == 0) {
+    const b200_send_op* ops = (const b200_send_op*)ops_v;
+    size_t total_slices = 0;
+    for (size_t i = 0; i < nops; i++) total_slices += ops[i].nslices;
+    std::vector<SendOpDev> h(nops);
+    std::vector<SliceDev> hs(total_slices ? total_slices : 1);
+    ok = CU_OK(cudaMalloc(&b->d_slices, sizeof(SliceDev) * hs.size())) &&
+         CU_OK(cudaMalloc(&b->d_ops, sizeof(SendOpDev) * (nops ? nops : 1)));
+    size_t off = 0;
+    for (size_t i = 0; ok && i < nops; i++) {
+      if (!ops[i].pair) {
+        set_err("batch: null pair");
+        ok = false;
+        break;
+      }
+      h[i].slot = ops[i].pair->slot;
+      h[i].flags = (uint32_t)(flags & B200_BATCH_UNTIL_BLOCKED);
+      h[i].slices = b->d_slices + off;
+      h[i].nslices = ops[i].nslices;
+      h[i].byte_idx = ops[i].byte_idx;
+      for (size_t j = 0; j < ops[i].nslices; j++) {
+        hs[off + j].ptr = (const uint8_t*)ops[i].slices[j].ptr;
+        hs[off + j].len = ops[i].slices[j].len;
+      }
+      off += ops[i].nslices;
+    }
+    ok = ok && CU_OK(cudaMemcpy(b->d_slices, hs.data(), sizeof(SliceDev) * hs.size(), cudaMemcpyHostToDevice)) &&
+         CU_OK(cudaMemcpy(b->d_ops, h.data(), sizeof(SendOpDev) * nops, cudaMemcpyHostToDevice));
+  } else {
+    const b200_recv_op* ops = (const b200_recv_op*)ops_v;
+    std::vector<RecvOpDev> h(nops);
+    ok = CU_OK(cudaMalloc(&b->d_ops, sizeof(RecvOpDev) * (nops ? nops : 1)));
+    for (size_t i = 0; ok && i < nops; i++) {
+      if (!ops[i].pair) {
+        set_err("batch: null pair");
+        ok = false;
+        break;
+      }
+      h[i].slot = ops[i].pair->slot;
+      h[i].flags = (uint32_t)(flags & B200_BATCH_UNTIL_BLOCKED);
+      h[i].dst = (uint8_t*)ops[i].dst;
+      h[i].cap = ops[i].cap;
+    }
+    ok = ok && CU_OK(cudaMemcpy(b->d_ops, h.data(), sizeof(RecvOpDev) * nops, cudaMemcpyHostToDevice));
+  }
+  ok = ok && CU_OK(cudaMalloc(&b->d_results, sizeof(OpResult) * (nops ? nops : 1))) &&
+       CU_OK(cudaHostAlloc(&b->h_results, sizeof(OpResult) * (nops ? nops : 1), cudaHostAllocPortable));
+  if (!ok) {
+    b200_batch_destroy(b);
+    return nullptr;
+  }
+  return b;
+}
+
+extern "C" b200_batch* b200_batch_prepare_send(const b200_send_op* ops, size_t nops, int flags) {
+  return prepare_common(0, ops, nops, flags);
+}
+extern "C" b200_batch* b200_batch_prepare_recv(const b200_recv_op* ops, size_t nops, int flags) {
+  return prepare_common(1, ops, nops, flags);
+}
+
+extern "C" int b200_batch_launch(b200_batch* b, void* stream) {
+  if (!b) return -1;
+  Runtime& r = R();
+  cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
+  if (b->nops == 0) return 0;
+  if (b->kind == 0) launch_send(r.d_pairs, (const SendOpDev*)b->d_ops, b->d_results, b->nops, s);
+  else launch_recv(r.d_pairs, (const RecvOpDev*)b->d_ops, b->d_results, b->nops, s);
+  r.launches++;
+  return CU_OK(cudaGetLastError()) ? 0 : -1;
+}
+
+extern "C" int b200_batch_results(b200_batch* b, uint64_t* out, void* stream) {
+  if (!b) return -1;
+  Runtime& r = R();
+  cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
+  if (b->nops == 0) return 0;
+  if (!CU_OK(cudaMemcpyAsync(b->h_results, b->d_results, sizeof(OpResult) * b->nops, cudaMemcpyDeviceToHost, s)) ||
+      !CU_OK(cudaStreamSynchronize(s)))
+    return -1;
+  if (out)
+    for (int i = 0; i < b->nops; i++) out[i] = b->h_results[i].bytes;
+  return 0;
+}
+
+extern "C" int b200_batch_calls(b200_batch* b, uint64_t* out) {
+  if (!b || !out) return -1;
+  for (int i = 0; i < b->nops; i++) out[i] = b->h_results[i].calls;
+  return 0;
+}
+
+extern "C" void b200_batch_destroy(b200_batch* b) {
+  if (!b) return;
+  if (b->d_ops) cudaFree(b->d_ops);
+  if (b->d_slices) cudaFree(b->d_slices);
+  if (b->d_results) cudaFree(b->d_results);
+  if (b->h_results) cudaFreeHost(b->h_results);
+  delete b;
+}
+
+static int run_unprepared(int kind, const void* ops, size_t nops, int flags, uint64_t* out, void* stream) {
+  b200_batch* b = prepare_common(kind, ops, nops, flags);
+  if (!b) return -1;
+  int rc = b200_batch_launch(b, stream);
+  // descriptors live in HBM owned by the batch object, so even the ASYNC form
+  // has to wait before they are released
+  if (rc == 0) rc = b200_batch_results(b, out, stream);
+  b200_batch_destroy(b);
+  return rc;
+}
+
+extern "C" int b200_pairs_send(const b200_send_op* ops, size_t nops, int flags, uint64_t* accepted, void* stream) {
+  return run_unprepared(0, ops, nops, flags, accepted, stream);
+}
+extern "C" int b200_pairs_recv(const b200_recv_op* ops, size_t nops, int flags, uint64_t* delivered, void* stream) {
+  return run_unprepared(1, ops, nops, flags, delivered, stream);
+}
+
+// ==================================================================== poller
+
+extern "C" int b200_poller_scan(b200_pair* const* pairs, size_t n, uint32_t* events) {
+  if (!ensure_init()) return -1;
+  Runtime& r = R();
+  if (n > (size_t)kMaxPairs) return -1;
+  std::lock_guard<std::mutex> lk(r.scan_mu);
+  cudaSetDevice(r.dev);
+  for (size_t i = 0; i < n; i++) r.h_scan_slots[i] = pairs[i]->slot;
+  r.h_scan_count[0] = 0;
+  launch_poll_scan(r.d_pairs, r.h_scan_slots, r.h_scan_events, r.h_scan_count, r.h_scan_ready, (int)n,
+                   r.poll_stream);
+  r.launches++;
+  if (!CU_OK(cudaGetLastError()) || !CU_OK(cudaStreamSynchronize(r.poll_stream))) return -1;
+  if (events)
+    for (size_t i = 0; i < n; i++) events[i] = r.h_scan_events[i];
+  return (int)r.h_scan_count[0];
+}
+
+static void poller_main(int /*id*/) {
+  Runtime& r = R();
+  std::vector<b200_pair*> snap;
+  std::vector<uint32_t> ev;
+  while (r.poll_running.load()) {
+    {
+      std::unique_lock<std::mutex> lk(r.pmu);
+      if (r.pollables.empty()) {  // poller.cc:58-63: sleep while there is nothing to poll
+        r.pcv.wait_for(lk, std::chrono::milliseconds(r.cfg.poller_sleep_ms),
+                       [&] { return !r.pollables.empty() || !r.poll_running.load(); });
+        continue;
+      }
+      snap = r.pollables;
+    }
+    ev.assign(snap.size(), 0);
+    int nready = b200_poller_scan(snap.data(), snap.size(), ev.data());
+    if (nready <= 0) continue;
+    for (size_t i = 0; i < snap.size(); i++) {
+      if (!ev[i]) continue;
+      struct pollfd pfd = {snap[i]->wakeup_fd, POLLIN, 0};
+      if (poll(&pfd, 1, 0) <= 0) kick(snap[i]);  // skip a pair whose eventfd is already signalled (poller.cc:73-75)
+    }
+  }
+}
+
+extern "C" void b200_poller_add(b200_pair* p) {
+  if (!p || !ensure_init()) return;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.pmu);
+  if ((int)r.pollables.size() >= B200_POLLER_CAPACITY) return;  // poller.cc:13 asserts
+  for (b200_pair* q : r.pollables)
+    if (q == p) return;
+  r.pollables.push_back(p);
+  p->in_poller = true;
+  if (!r.poll_running.load()) {
+    r.poll_running = true;
+    for (int i = 0; i < r.cfg.poller_threads; i++) r.poll_threads.emplace_back(poller_main, i);
+  }
+  r.pcv.notify_all();
+}
+
+extern "C" void b200_poller_remove(b200_pair* p) {
+  if (!p) return;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.pmu);
+  for (size_t i = 0; i < r.pollables.size(); i++) {
+    if (r.pollables[i] == p) {
+      r.pollables.erase(r.pollables.begin() + i);
+      break;
+    }
+  }
+  p->in_poller = false;
+}
+
+extern "C" void b200_poller_shutdown(void) {
+  Runtime& r = R();
+  if (!r.poll_running.exchange(false)) return;
+  {
+    std::lock_guard<std::mutex> lk(r.pmu);
+    r.pcv.notify_all();
+  }
+  for (auto& t : r.poll_threads) t.join();
+  r.poll_threads.clear();
+}

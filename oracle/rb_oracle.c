@@ -277,7 +277,7 @@ uint64_t orb_pair_recv_drain(orb_pair* p, void* dst, uint64_t cap, uint64_t* cal
 /* ------------------------------------------------- multi-threaded CPU baseline */
 
 typedef struct {
-  int first_conn, n_conn, msgs;
+  int first_conn, n_conn, warm, msgs;
   uint64_t ring_capacity;
   const uint64_t* lens;
   size_t nslices;
@@ -313,9 +313,12 @@ static void* orb_worker_main(void* arg) {
       src[c][i] = (uint8_t)(i + 131u * (unsigned)(w->first_conn + c));
     memset(dst[c], 0, msg_bytes);
   }
-  pthread_barrier_wait(w->start);
   uint64_t delivered = 0;
-  for (int m = 0; m < w->msgs; m++) {
+  for (int m = -w->warm; m < w->msgs; m++) {
+    if (m == 0) {
+      pthread_barrier_wait(w->start); /* warm-up messages done: timing starts */
+      delivered = 0;
+    }
     for (int c = 0; c < nc; c++) {
       uint64_t off = 0;
       for (size_t i = 0; i < w->nslices; i++) {
@@ -356,7 +359,7 @@ static void* orb_worker_main(void* arg) {
   return NULL;
 }
 
-double orb_bench_stream(int conns, int threads, int msgs, uint64_t ring_capacity,
+double orb_bench_stream(int conns, int threads, int warm, int msgs, uint64_t ring_capacity,
                         const uint64_t* lens, size_t nslices, uint64_t* delivered,
                         uint64_t* checksum) {
   if (threads < 1) threads = 1;
@@ -370,6 +373,7 @@ double orb_bench_stream(int conns, int threads, int msgs, uint64_t ring_capacity
     int nc = conns / threads + (t < conns % threads ? 1 : 0);
     ws[t].first_conn = base;
     ws[t].n_conn = nc;
+    ws[t].warm = warm;
     ws[t].msgs = msgs;
     ws[t].ring_capacity = ring_capacity;
     ws[t].lens = lens;

@@ -122,11 +122,11 @@ uint64_t orb_pair_send_all(orb_pair* p, const orb_slice* slices, size_t n,
 uint64_t orb_pair_recv_drain(orb_pair* p, void* dst, uint64_t cap, uint64_t* calls);
 
 /* Multi-threaded CPU baseline over this port: `conns` loopback connections,
- * each sending `msgs` messages built from the chttp2-shaped slice list
+ * each sending `warm` untimed then `msgs` timed messages built from the chttp2-shaped slice list
  * (lens[0..nslices)) out of `src` and draining them into `dst`; `threads`
  * pthreads each own conns/threads connections.  Returns elapsed seconds
  * (wall), fills *delivered with payload bytes delivered. */
-double orb_bench_stream(int conns, int threads, int msgs, uint64_t ring_capacity,
+double orb_bench_stream(int conns, int threads, int warm, int msgs, uint64_t ring_capacity,
                         const uint64_t* lens, size_t nslices, uint64_t* delivered,
                         uint64_t* checksum);
 

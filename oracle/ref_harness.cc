@@ -229,7 +229,7 @@ uint64_t ref_ring_write_frames(void* r, uint64_t tail, uint8_t* staging, const h
 // Same workload shape as orb_bench_stream (oracle/rb_oracle.c) but through the
 // reference's PairPollable::Send/Recv.
 struct ref_worker {
-  int first_conn, n_conn, msgs;
+  int first_conn, n_conn, warm, msgs;
   const uint64_t* lens;
   size_t nslices;
   uint64_t delivered, checksum;
@@ -262,9 +262,12 @@ static void* ref_worker_main(void* arg) {
     for (uint64_t i = 0; i < msg_bytes; i++)
       src[c][i] = static_cast<uint8_t>(i + 131u * static_cast<unsigned>(w->first_conn + c));
   }
-  pthread_barrier_wait(w->bar);
   uint64_t delivered = 0;
-  for (int m = 0; m < w->msgs; m++) {
+  for (int m = -w->warm; m < w->msgs; m++) {
+    if (m == 0) {
+      pthread_barrier_wait(w->bar);  // warm-up messages done: timing starts
+      delivered = 0;
+    }
     for (int c = 0; c < nc; c++) {
       uint64_t off = 0;
       for (size_t i = 0; i < w->nslices; i++) {
@@ -305,7 +308,7 @@ static void* ref_worker_main(void* arg) {
   return nullptr;
 }
 
-double ref_bench_stream(int conns, int threads, int msgs, uint64_t ring_capacity,
+double ref_bench_stream(int conns, int threads, int warm, int msgs, uint64_t ring_capacity,
                         const uint64_t* lens, size_t nslices, uint64_t* delivered,
                         uint64_t* checksum) {
   ref_set_ring_kb(static_cast<uint32_t>(ring_capacity / 1024));
@@ -318,7 +321,7 @@ double ref_bench_stream(int conns, int threads, int msgs, uint64_t ring_capacity
   int base = 0;
   for (int t = 0; t < threads; t++) {
     int nc = conns / threads + (t < conns % threads ? 1 : 0);
-    ws[t] = ref_worker{base, nc, msgs, lens, nslices, 0, 0, &bar};
+    ws[t] = ref_worker{base, nc, warm, msgs, lens, nslices, 0, 0, &bar};
     base += nc;
     pthread_create(&th[t], nullptr, ref_worker_main, &ws[t]);
   }

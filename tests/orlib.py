@@ -92,7 +92,7 @@ class Oracle:
             ("orb_pair_disconnect", None, [C.POINTER(OrbPair)]),
             ("orb_pair_send_all", u64, [C.POINTER(OrbPair), C.POINTER(Slice), C.c_size_t, C.c_size_t, C.POINTER(u64)]),
             ("orb_pair_recv_drain", u64, [C.POINTER(OrbPair), C.c_void_p, u64, C.POINTER(u64)]),
-            ("orb_bench_stream", C.c_double, [C.c_int, C.c_int, C.c_int, u64, C.POINTER(u64), C.c_size_t,
+            ("orb_bench_stream", C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, u64, C.POINTER(u64), C.c_size_t,
                                               C.POINTER(u64), C.POINTER(u64)]),
         ]:
             f = getattr(L, name)
@@ -158,10 +158,10 @@ class Oracle:
     def disconnect(self, p):
         self.L.orb_pair_disconnect(p)
 
-    def bench_stream(self, conns, threads, msgs, ring_capacity, lens):
+    def bench_stream(self, conns, threads, warm, msgs, ring_capacity, lens):
         lens = np.ascontiguousarray(lens, dtype=np.uint64)
         d, h = C.c_uint64(0), C.c_uint64(0)
-        t = self.L.orb_bench_stream(conns, threads, msgs, ring_capacity, _u64p(lens), lens.size,
+        t = self.L.orb_bench_stream(conns, threads, warm, msgs, ring_capacity, _u64p(lens), lens.size,
                                     C.byref(d), C.byref(h))
         return t, d.value, h.value
 
@@ -202,7 +202,7 @@ class Ref:
             ("ref_encoded_size", u64, [u64]), ("ref_calc_writable", u64, [u64]),
             ("ref_free_size", u64, [vp, u64, u64]),
             ("ref_ring_write_frames", u64, [vp, u64, vp, C.POINTER(Slice), C.c_size_t, C.POINTER(C.c_int)]),
-            ("ref_bench_stream", C.c_double, [C.c_int, C.c_int, C.c_int, u64, C.POINTER(u64), C.c_size_t,
+            ("ref_bench_stream", C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, u64, C.POINTER(u64), C.c_size_t,
                                               C.POINTER(u64), C.POINTER(u64)]),
         ]:
             f = getattr(L, fname)
@@ -269,9 +269,9 @@ class Ref:
     def disconnect(self, p):
         self.L.ref_pair_disconnect(p)
 
-    def bench_stream(self, conns, threads, msgs, ring_capacity, lens):
+    def bench_stream(self, conns, threads, warm, msgs, ring_capacity, lens):
         lens = np.ascontiguousarray(lens, dtype=np.uint64)
         d, h = C.c_uint64(0), C.c_uint64(0)
-        t = self.L.ref_bench_stream(conns, threads, msgs, ring_capacity, _u64p(lens), lens.size,
+        t = self.L.ref_bench_stream(conns, threads, warm, msgs, ring_capacity, _u64p(lens), lens.size,
                                     C.byref(d), C.byref(h))
         return t, d.value, h.value
