@@ -216,11 +216,11 @@ def main():
     pairs = [pkg.connected_pair("c%d-%d-tx" % (rank, c), "c%d-%d-rx" % (rank, c)) for c in range(conns)]
 
     # synthetic payload resident in HBM: b[i] = f(i, connection), > L2 (1 GiB src, 4 GiB of rings)
-    src = torch.empty(conns * total, dtype=torch.uint8, device=dev)
     i = torch.arange(total, device=dev, dtype=torch.int64)
-    for c in range(conns):
-        src[c * total:(c + 1) * total] = (((i * 2654435761 >> 11) + 131 * (rank * conns + c)) & 255).to(torch.uint8)
-    del i
+    row = (((i * 2654435761) >> 11) & 255).to(torch.uint8)                       # b[i]
+    offs = ((torch.arange(conns, device=dev, dtype=torch.int64) + rank * conns) * 131 & 255).to(torch.uint8)
+    src = (row[None, :] + offs[:, None]).reshape(-1)                             # + 131*c (mod 256), one kernel
+    del i, row, offs
     dst = torch.zeros(conns * total, dtype=torch.uint8, device=dev)
 
     def build_batches(src_ptr, dst_ptr):
@@ -237,8 +237,12 @@ def main():
         return pkg.Batch("send", sops, pkg.UNTIL_BLOCKED), pkg.Batch("recv", rops, pkg.UNTIL_BLOCKED), keep
 
     bs, br, keep = build_batches(src.data_ptr(), dst.data_ptr())
-    stream = torch.cuda.current_stream()
+    # an explicit stream: the library treats a NULL stream handle as "its own stream", and
+    # torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sh = C.c_void_p(stream.cuda_stream)
+    assert sh.value, "need a non-default stream handle"
 
     def step():
         bs.launch(sh)

@@ -228,188 +228,216 @@ __device__ __forceinline__ void publish_mirror(PairMirror* m, const PairDev* P, 
 // =========================================================================
 // k_send
 // =========================================================================
+//
+// One CTA per (pair, write).  Warp 0 plans Send() call j+1 (credit snapshot,
+// warp scan of encoded sizes, cut detection) while all warps -- warp 0 joins
+// once the plan is published -- move the bytes of call j in 4 KiB work items
+// claimed from a shared counter.  One CTA barrier per call; footers of call j
+// are written after that barrier (everything else of the call is fenced before).
 
-constexpr int kSendThreads = 256;
-constexpr uint64_t kChunk = 16384;  // bytes of payload one warp moves per work item
+constexpr int kSendThreads = 512;
+constexpr uint32_t kChunk = 4096;  // payload bytes per work item
 
 struct FrameDesc {
   const uint8_t* src;
   uint64_t len;   // payload bytes
   uint64_t off;   // ring offset of the frame header
-  uint32_t first_item;  // prefix of work items
+  uint32_t first_item;
   uint32_t _pad;
 };
 
-struct SendShared {
-  uint64_t rt, rh, cap, staging, total_left, written_total, ncalls;
-  uint64_t cur, bidx;
-  uint32_t nframes, nitems, stop, partial, status, max_sge;
+struct SendCall {
   FrameDesc frames[kMaxSgeLimit];
+  uint32_t nframes, nitems, last, _pad;
 };
 
-__global__ void __launch_bounds__(kSendThreads, 3)
+struct SendPlanState {  // touched by warp 0 only
+  uint64_t rt, cap, staging, total_left, written_total, ncalls, cur, bidx;
+  uint32_t partial, max_sge;
+};
+
+// One PairPollable::Send call (pair.cc:645-734) as integer planning; executed by
+// warp 0, all lanes converged.  Returns true when this was the last call.
+__device__ __forceinline__ void plan_send_call(const SendOpDev& op, const PairDev* P, SendPlanState& S,
+                                               SendCall& out, uint32_t lane) {
+  const uint64_t cap = S.cap, mask = cap - 1, rt = S.rt;
+  const uint64_t rh = ld_acquire_u64(&P->credit_head);  // credit snapshot, once per call (pair.cc:650)
+  const uint64_t cur = S.cur, bidx = S.bidx;
+  const uint64_t idx = cur + lane;
+  const bool valid = lane < S.max_sge && idx < op.nslices;
+  const uint8_t* ptr = nullptr;
+  uint64_t len = 0;
+  if (valid) {
+    SliceDev sl = op.slices[idx];
+    uint64_t skip = lane == 0 ? bidx : 0;
+    ptr = sl.ptr + skip;
+    len = sl.len - skip;
+  }
+  const uint64_t e = valid ? encoded_size(len) : 0;
+  uint64_t incl = e;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  const uint64_t a = incl - e;  // staging / ring bytes consumed before this slice
+  // min(CWS(send_buf_free), CWS(recv_buf_free)) (pair.cc:676-681): both shrink by `a`
+  const uint64_t fr = free_size(cap, rh, rt);
+  const uint64_t lim = S.staging < fr ? S.staging : fr;
+  const uint64_t room = calc_writable(lim > a ? lim - a : 0);
+  const bool fits = valid && len != 0 && len <= room;
+  const unsigned bad = __ballot_sync(0xffffffffu, !fits);
+  const int first_bad = __ffs(bad) - 1;
+  const int nfull = first_bad < 0 ? 32 : first_bad;
+  uint64_t p = 0;
+  if ((int)lane < nfull) p = len;
+  else if ((int)lane == nfull && valid && len != 0) p = room;  // cut: space ran out
+  const unsigned fmask = __ballot_sync(0xffffffffu, p != 0);
+  const uint32_t nframes = __popc(fmask);
+  uint64_t wsum = p, esum = p ? encoded_size(p) : 0;
+  const uint32_t items = p ? (uint32_t)((p + kChunk - 1) / kChunk) : 0;
+  uint32_t items_incl = items;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, items_incl, o);
+    if (lane >= (uint32_t)o) items_incl += t;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    esum += __shfl_xor_sync(0xffffffffu, esum, o);
+  }
+  if (p) {
+    FrameDesc& f = out.frames[lane];  // frames are lanes 0..nframes-1
+    f.src = ptr;
+    f.len = p;
+    f.off = (rt + a) & mask;
+    f.first_item = items_incl - items;
+  }
+  const uint32_t nitems = __shfl_sync(0xffffffffu, items_incl, 31);
+  const uint64_t cut_p = __shfl_sync(0xffffffffu, p, nfull < 32 ? nfull : 0);
+  if (lane == 0) {
+    out.nframes = nframes;
+    out.nitems = nitems;
+    S.rt = (rt + esum) & mask;
+    S.partial = wsum < S.total_left;  // pair.cc:712
+    S.total_left -= wsum;
+    S.written_total += wsum;
+    if (wsum) S.ncalls++;
+    // cursor advance (rdma_flush, rdma_bp_posix.cc:480-493)
+    uint64_t nb = 0;
+    if (nfull < 32 && nframes > (uint32_t)nfull) nb = (nfull == 0 ? bidx : 0) + cut_p;  // cut slice stays current
+    else if (nfull == 0) nb = bidx;                                                    // nothing consumed
+    S.cur = cur + nfull;
+    S.bidx = nb;
+    out.last = (wsum == 0) || !(op.flags & kFlagUntilBlocked) || S.total_left == 0;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSendThreads, 2)
 k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult* __restrict__ results) {
-  __shared__ SendShared S;
+  __shared__ SendCall calls[2];
+  __shared__ SendPlanState PS;
   __shared__ unsigned long long s_total;
+  __shared__ uint32_t s_next[2];
+  __shared__ uint32_t s_status;
   const SendOpDev op = ops[blockIdx.x];
   PairDev* P = &pairs[op.slot];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t nwarps = kSendThreads / 32;
 
   if (tid == 0) {
     s_total = 0;
-    S.rt = P->remote_tail;
-    S.cap = P->cap;
-    S.staging = P->cap / 2;  // send_buf_size = recv_buf_size / 2, pair.cc:104
-    S.status = P->status;
-    S.max_sge = P->max_sge;
-    S.cur = 0;
-    S.bidx = op.byte_idx;
-    S.written_total = 0;
-    S.ncalls = 0;
-    S.partial = P->partial_write;
-    S.stop = 0;
+    s_next[0] = s_next[1] = 0;
+    s_status = P->status;
+    PS.rt = P->remote_tail;
+    PS.cap = P->cap;
+    PS.staging = P->cap / 2;  // send_buf_size = recv_buf_size / 2, pair.cc:104
+    PS.max_sge = P->max_sge;
+    PS.cur = 0;
+    PS.bidx = op.byte_idx;
+    PS.written_total = 0;
+    PS.ncalls = 0;
+    PS.partial = P->partial_write;
   }
   __syncthreads();
-  // total_slice_size, pair.cc:661-664
-  {
+  {  // total_slice_size, pair.cc:661-664
     unsigned long long part = 0;
     for (uint64_t i = tid; i < op.nslices; i += kSendThreads) part += op.slices[i].len;
     for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
     if (lane == 0 && part) atomicAdd(&s_total, part);
   }
   __syncthreads();
-  if (tid == 0) S.total_left = s_total - op.byte_idx;
-  __syncthreads();
-
-  if (S.status != kStConnected) {  // pair.cc:657
+  if (s_status != kStConnected) {  // pair.cc:657
     if (tid == 0) {
       results[blockIdx.x].bytes = 0;
       results[blockIdx.x].calls = 0;
     }
     return;
   }
-  const uint64_t mask = S.cap - 1;
+  if (tid == 0) PS.total_left = s_total - op.byte_idx;
+  __syncthreads();
+  const uint64_t cap = PS.cap, mask = cap - 1;
   uint8_t* ring = P->peer_ring;
   const bool sys_scope = P->wire != 0;
 
-  while (true) {
-    // ------------------------------------------------ plan one Send() call
-    if (warp == 0) {
-      const uint64_t cap = S.cap, rt = S.rt;
-      // credit snapshot, once per call (pair.cc:650)
-      const uint64_t rh = ld_acquire_u64(&P->credit_head);
-      const uint64_t cur = S.cur, bidx = S.bidx;
-      const uint64_t idx = cur + lane;
-      bool valid = lane < S.max_sge && idx < op.nslices;
-      const uint8_t* ptr = nullptr;
-      uint64_t len = 0;
-      if (valid) {
-        SliceDev sl = op.slices[idx];
-        uint64_t skip = lane == 0 ? bidx : 0;
-        ptr = sl.ptr + skip;
-        len = sl.len - skip;
-      }
-      uint64_t e = valid ? encoded_size(len) : 0;
-      uint64_t incl = e;  // inclusive scan of encoded sizes
-      for (int o = 1; o < 32; o <<= 1) {
-        uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const uint64_t a = incl - e;  // bytes of staging / ring consumed before this slice
-      // min(CWS(send_buf_free), CWS(recv_buf_free)): both shrink by `a`
-      const uint64_t fr = free_size(cap, rh, rt);
-      const uint64_t lim = S.staging < fr ? S.staging : fr;
-      const uint64_t room = calc_writable(lim > a ? lim - a : 0);
-      const bool fits = valid && len != 0 && len <= room;
-      const unsigned bad = __ballot_sync(0xffffffffu, !fits);  // invalid lanes count as bad
-      const int first_bad = __ffs(bad) - 1;                    // lane 31 valid+fits => bad==0 => -1
-      const int nfull = first_bad < 0 ? 32 : first_bad;
-      uint64_t p = 0;
-      if ((int)lane < nfull) p = len;
-      else if ((int)lane == nfull && valid && len != 0) p = room;  // cut: space ran out (pair.cc:676-681)
-      const unsigned fmask = __ballot_sync(0xffffffffu, p != 0);
-      const uint32_t nframes = __popc(fmask);
-      uint64_t wsum = p, esum = p ? encoded_size(p) : 0;
-      uint32_t items = p ? (uint32_t)((p + kChunk - 1) / kChunk) : 0;
-      uint32_t items_incl = items;
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, items_incl, o);
-        if (lane >= o) items_incl += t;
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-        esum += __shfl_xor_sync(0xffffffffu, esum, o);
-      }
-      if (p) {
-        FrameDesc& f = S.frames[lane];  // frames are lanes 0..nframes-1 (contiguous)
-        f.src = ptr;
-        f.len = p;
-        f.off = (rt + a) & mask;
-        f.first_item = items_incl - items;
-      }
-      const uint32_t nitems = __shfl_sync(0xffffffffu, items_incl, 31);
-      // cursor advance (rdma_flush, rdma_bp_posix.cc:480-493)
-      const uint64_t cut_p = __shfl_sync(0xffffffffu, p, nfull < 32 ? nfull : 0);
-      if (lane == 0) {
-        S.nframes = nframes;
-        S.nitems = nitems;
-        S.rt = (rt + esum) & mask;
-        S.partial = wsum < S.total_left;  // pair.cc:712
-        S.total_left -= wsum;
-        S.written_total += wsum;
-        if (wsum) S.ncalls++;
-        uint64_t ncur = cur + nfull, nb = 0;
-        if (nfull < 32 && nframes > (uint32_t)nfull) {  // the cut slice stays current
-          nb = (nfull == 0 ? bidx : 0) + cut_p;
-        } else if (nfull == 0) {
-          nb = bidx;  // nothing consumed
-        }
-        S.cur = ncur;
-        S.bidx = nb;
-        S.stop = (wsum == 0) || !(op.flags & kFlagUntilBlocked) || S.total_left == 0;
+  if (warp == 0) plan_send_call(op, P, PS, calls[0], lane);
+  __syncthreads();
+
+  for (uint32_t j = 0;; j++) {
+    SendCall& cur = calls[j & 1];
+    const bool last = cur.last != 0;
+    // footers of the previous call: everything else of it was fenced before the barrier.
+    // A frame is complete for the reader only when header != 0 and footer == ~0
+    // (ring_buffer.cc:75-96), so the footer goes last.
+    if (j > 0) {
+      const SendCall& prev = calls[(j - 1) & 1];
+      if (tid >= 32 && tid - 32 < prev.nframes) {
+        const FrameDesc fd = prev.frames[tid - 32];
+        *reinterpret_cast<uint64_t*>(ring + ((fd.off + 8 + round_up8(fd.len)) & mask)) = kFooter;
       }
     }
-    __syncthreads();
-    const uint32_t nframes = S.nframes, nitems = S.nitems;
-    // ------------------------------------------------ move the bytes
-    for (uint32_t w = warp; w < nitems; w += nwarps) {
+    __syncthreads();  // prev.frames fully consumed before warp 0 overwrites that buffer
+    if (warp == 0 && !last) plan_send_call(op, P, PS, calls[(j + 1) & 1], lane);
+    // ---------------------------------------------- move the bytes of call j
+    const uint32_t nframes = cur.nframes, nitems = cur.nitems;
+    while (true) {
+      uint32_t w = 0;
+      if (lane == 0) w = atomicAdd(&s_next[j & 1], 1u);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w >= nitems) break;
       uint32_t f = 0;
-      while (f + 1 < nframes && S.frames[f + 1].first_item <= w) f++;
-      const FrameDesc fd = S.frames[f];
+      while (f + 1 < nframes && cur.frames[f + 1].first_item <= w) f++;
+      const FrameDesc fd = cur.frames[f];
       const uint64_t c0 = (uint64_t)(w - fd.first_item) * kChunk;
       uint64_t n = fd.len - c0;
       if (n > kChunk) n = kChunk;
       if (c0 == 0 && lane == 0) *reinterpret_cast<uint64_t*>(ring + fd.off) = fd.len;  // AppendHeader
-      uint64_t pos = (fd.off + 8 + c0) & mask;
-      uint64_t seg1 = S.cap - pos;
+      const uint64_t pos = (fd.off + 8 + c0) & mask;
+      uint64_t seg1 = cap - pos;
       if (seg1 > n) seg1 = n;
       coop_copy<false>(ring + pos, fd.src + c0, seg1, lane, 32);
       if (n > seg1) coop_copy<false>(ring, fd.src + c0 + seg1, n - seg1, lane, 32);  // wrap: WR1 at remote+0
     }
-    // footer last: a frame is complete for the reader only when header != 0 and
-    // footer == ~0 (ring_buffer.cc:75-96), so everything else must be visible first
     if (sys_scope) __threadfence_system();
     else __threadfence();
     __syncthreads();
-    if (tid < nframes) {
-      const FrameDesc fd = S.frames[tid];
-      *reinterpret_cast<uint64_t*>(ring + ((fd.off + 8 + round_up8(fd.len)) & mask)) = kFooter;
+    if (tid == 0) s_next[j & 1] = 0;
+    if (last) {
+      if (tid < nframes) {
+        const FrameDesc fd = cur.frames[tid];
+        *reinterpret_cast<uint64_t*>(ring + ((fd.off + 8 + round_up8(fd.len)) & mask)) = kFooter;
+      }
+      break;
     }
-    const bool stop = S.stop;
-    __syncthreads();
-    if (stop) break;
   }
-
+  __syncthreads();
   if (tid == 0) {
-    P->remote_tail = S.rt;
-    P->partial_write = S.partial;
-    results[blockIdx.x].bytes = S.written_total;
-    results[blockIdx.x].calls = S.ncalls;
+    P->remote_tail = PS.rt;
+    P->partial_write = PS.partial;
+    results[blockIdx.x].bytes = PS.written_total;
+    results[blockIdx.x].calls = PS.ncalls;
     publish_mirror(P->mirror, P, P->mirror ? ((volatile PairMirror*)P->mirror)->has_message : 0,
                    P->mirror ? ((volatile PairMirror*)P->mirror)->readable : 0);
     // loopback wire: the peer lives in this table, refresh its readiness hint
-    if (P->peer_slot >= 0 && S.written_total) {
+    if (P->peer_slot >= 0 && PS.written_total) {
       __threadfence();
       PairDev* Q = &pairs[P->peer_slot];
       uint32_t hm;
@@ -429,37 +457,148 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
 // =========================================================================
 // k_recv
 // =========================================================================
+//
+// One CTA per (pair, read).  The frames of a ring form a linked list (the next
+// header sits right after the previous footer), so warp 0 is a scout: it walks
+// the list through a 256-byte register window (one 8-byte word per lane, so a
+// 9-byte HTTP/2 header frame and the header of the payload frame behind it cost
+// a single trip to memory), applies the Read/Recv integer logic and queues
+// batches of frames.  While the scout walks batch b+1, all warps scatter batch b
+// in 4 KiB work items: load, store to the destination slice, __syncwarp, then
+// clear exactly the ring bytes this warp just read (clear-on-read is part of
+// the wire protocol, ring_buffer.cc:146,160,180).  One CTA barrier per batch.
 
-constexpr int kRecvThreads = 256;
+constexpr int kRecvThreads = 512;
+constexpr int kBatchFrames = 32;
+constexpr uint64_t kBatchBytes = 192 * 1024;  // close a batch once this much payload is queued
 
-struct RecvShared {
-  uint64_t head, mh, remain, acc, cap;
-  uint64_t delivered, cap_left, ncalls;
-  // current call
-  uint64_t n, src_off, zstart, zlen, credit_val;
-  uint32_t credit_flag, stop, status;
+struct RecvFrame {
+  uint64_t src_off;   // ring offset of the first payload byte to deliver
+  uint64_t n;         // bytes to deliver
+  uint64_t dst_off;   // offset in the destination
+  uint32_t zhead;     // bytes to clear before the payload (the header word on first touch)
+  uint32_t ztail;     // bytes to clear after it (pad + footer once the frame is finished)
+  uint32_t first_item;
+  uint32_t _pad;
 };
 
-__global__ void __launch_bounds__(kRecvThreads, 3)
+struct RecvBatch {
+  RecvFrame f[kBatchFrames];
+  uint64_t credit_val;
+  uint32_t nframes, nitems, credit_flag, last;
+};
+
+struct ScoutState {  // registers of warp 0, uniform across lanes
+  uint64_t head, mh, remain, acc, cap_left, delivered, ncalls;
+  uint64_t win, win_base;
+  bool win_valid;
+};
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const void* p) {
+  uint64_t v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// 8-byte word at ring offset `off` through the scout's window
+__device__ __forceinline__ uint64_t scout_peek(ScoutState& st, const uint8_t* ring, uint64_t mask, uint64_t off,
+                                               uint32_t lane) {
+  uint64_t d = (off - st.win_base) & mask;
+  if (!st.win_valid || d >= 256) {
+    st.win_base = off;
+    st.win = ld_volatile_u64(ring + ((off + 8ull * lane) & mask));
+    st.win_valid = true;
+    d = 0;
+  }
+  return __shfl_sync(0xffffffffu, st.win, (int)(d >> 3));
+}
+
+// Queue the next batch: RingBufferPollable::Read (ring_buffer.cc:122-191) + PairPollable::Recv's
+// credit rule (pair.cc:276-284) as integer logic over the frame list.
+__device__ __forceinline__ void scout_batch(ScoutState& st, const uint8_t* ring, uint64_t cap, const RecvOpDev& op,
+                                            RecvBatch& out, uint32_t lane) {
+  const uint64_t mask = cap - 1;
+  uint32_t nframes = 0, nitems = 0, credit = 0, last = 0;
+  uint64_t bytes = 0, credit_val = 0;
+  while (nframes < (uint32_t)kBatchFrames && bytes < kBatchBytes) {
+    uint64_t r;
+    bool opening = false;
+    if (st.remain > 0) {
+      r = st.remain;
+    } else {  // GetReadableSize, ring_buffer.cc:67-97
+      const uint64_t hdr = scout_peek(st, ring, mask, st.head, lane);
+      if (hdr == 0 || hdr > cap - kReserved) { last = 1; break; }
+      const uint64_t foot = scout_peek(st, ring, mask, (st.head + 8 + round_up8(hdr)) & mask, lane);
+      if (foot != kFooter) { last = 1; break; }
+      r = hdr;
+      opening = true;
+    }
+    const uint64_t n = r < st.cap_left ? r : st.cap_left;
+    if (n == 0) { last = 1; break; }
+    if (opening) {  // first touch of this frame, ring_buffer.cc:135-147
+      st.mh = (st.head + 8) & mask;
+      st.head = (st.head + 16 + round_up8(r)) & mask;
+    }
+    const uint64_t src_off = st.mh;
+    st.mh = (st.mh + n) & mask;
+    st.remain = r - n;
+    uint32_t ztail = 0;
+    if (st.remain == 0) {  // pad + footer, ring_buffer.cc:170-183
+      const uint64_t up = round_up8(st.mh);
+      ztail = (uint32_t)(up - st.mh) + 8;
+      st.mh = ((up & mask) + 8) & mask;
+    }
+    const uint32_t zhead = opening ? 8u : 0u;
+    const uint32_t items = (uint32_t)((n + kChunk - 1) / kChunk);
+    if (lane == 0) {
+      RecvFrame& f = out.f[nframes];
+      f.src_off = src_off;
+      f.n = n;
+      f.dst_off = st.delivered;
+      f.zhead = zhead;
+      f.ztail = ztail;
+      f.first_item = nitems;
+    }
+    nframes++;
+    nitems += items;
+    bytes += n;
+    st.delivered += n;
+    st.cap_left -= n;
+    st.ncalls++;
+    st.acc += (uint64_t)zhead + n + ztail;  // internal_bytes_read of this call
+    if (st.acc >= cap / 2) {                // pair.cc:276-284: credit goes out after this batch is cleared
+      credit = 1;
+      credit_val = st.mh;
+      st.acc = 0;
+    }
+    if (!(op.flags & kFlagUntilBlocked) || st.cap_left == 0) { last = 1; break; }
+    if (credit) break;
+  }
+  if (lane == 0) {
+    out.nframes = nframes;
+    out.nitems = nitems;
+    out.credit_flag = credit;
+    out.credit_val = credit_val;
+    out.last = last;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kRecvThreads, 2)
 k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult* __restrict__ results) {
-  __shared__ RecvShared S;
+  __shared__ RecvBatch batches[2];
+  __shared__ uint32_t s_next[2];
+  __shared__ uint32_t s_status;
   const RecvOpDev op = ops[blockIdx.x];
   PairDev* P = &pairs[op.slot];
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    S.head = P->head;
-    S.mh = P->moving_head;
-    S.remain = P->remain;
-    S.acc = P->acc;
-    S.cap = P->cap;
-    S.status = P->status;
-    S.delivered = 0;
-    S.cap_left = op.cap;
-    S.ncalls = 0;
+    s_status = P->status;
+    s_next[0] = s_next[1] = 0;
   }
   __syncthreads();
-  if (S.status != kStConnected) {  // pair.cc:266-268
+  if (s_status != kStConnected) {  // pair.cc:266-268
     if (tid == 0) {
       results[blockIdx.x].bytes = 0;
       results[blockIdx.x].calls = 0;
@@ -467,100 +606,86 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
     return;
   }
   uint8_t* ring = P->ring;
-  const uint64_t cap = S.cap, mask = cap - 1;
+  const uint64_t cap = P->cap, mask = cap - 1;
 
-  while (true) {
-    // ------------------------------------------------ one Recv() call: plan
-    if (tid == 0) {
-      uint64_t r = 0;
-      bool opening = false;
-      if (S.remain > 0) {
-        r = S.remain;
-      } else {  // GetReadableSize, ring_buffer.cc:67-97
-        uint32_t hm;
-        rx_probe(ring, cap, S.head, 0, hm, r);
-        opening = r > 0;
-      }
-      uint64_t n = r < S.cap_left ? r : S.cap_left;
-      S.n = n;
-      S.credit_flag = 0;
-      if (n > 0) {
-        const uint64_t prev_mh = S.mh;
-        if (opening) {  // first touch of this frame, ring_buffer.cc:135-147
-          S.mh = (S.head + 8) & mask;
-          S.head = (S.head + 16 + round_up8(r)) & mask;
-        }
-        S.src_off = S.mh;
-        S.zstart = prev_mh;  // between frames moving_head == head: covers the header word too
-        S.mh = (S.mh + n) & mask;
-        S.remain = r - n;
-        if (S.remain == 0) {  // pad + footer, ring_buffer.cc:170-183
-          S.mh = round_up8(S.mh) & mask;
-          S.mh = (S.mh + 8) & mask;
-        }
-        const uint64_t internal = (S.mh + cap - prev_mh) & mask;
-        S.zlen = internal;  // everything retired this call gets cleared
-        S.acc += internal;
-        if (S.acc >= cap / 2) {  // pair.cc:276-284
-          S.credit_flag = 1;
-          S.credit_val = S.mh;
-          S.acc = 0;
-        }
-        S.ncalls++;
-      }
-      S.stop = (n == 0) || !(op.flags & kFlagUntilBlocked) || (S.cap_left - n == 0);
-    }
-    __syncthreads();
-    const uint64_t n = S.n;
-    if (n == 0) break;
-    // ------------------------------------------------ scatter payload
-    {
-      uint8_t* dst = op.dst + S.delivered;
-      const uint64_t pos = S.src_off;
-      uint64_t seg1 = cap - pos;
-      if (seg1 > n) seg1 = n;
-      coop_copy<true>(dst, ring + pos, seg1, tid, kRecvThreads);
-      if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, tid, kRecvThreads);
-    }
-    __syncthreads();  // every load of this call is done before anything is cleared
-    // ------------------------------------------------ clear-on-read
-    {
-      const uint64_t z0 = S.zstart, zl = S.zlen;
-      uint64_t seg1 = cap - z0;
-      if (seg1 > zl) seg1 = zl;
-      coop_zero(ring + z0, seg1, tid, kRecvThreads);
-      if (zl > seg1) coop_zero(ring, zl - seg1, tid, kRecvThreads);
-    }
-    const bool credit = S.credit_flag != 0;
-    if (credit) {  // the sender may reuse the space only once it reads as zero
-      __threadfence_system();
-      __syncthreads();
-      if (tid == 0) {
-        // updateStatus, pair.cc:624-641: 16-byte status_report to the peer
-        st_release_v2u64(P->peer_credit, S.credit_val, 0);
-        if (P->peer_mirror) ((volatile PairMirror*)P->peer_mirror)->credit_head = S.credit_val;
-      }
-    }
-    const bool stop = S.stop;
-    __syncthreads();
-    if (tid == 0) {
-      S.delivered += n;
-      S.cap_left -= n;
-    }
-    if (stop) break;
-    __syncthreads();
+  ScoutState st;
+  if (warp == 0) {
+    st.head = P->head;
+    st.mh = P->moving_head;
+    st.remain = P->remain;
+    st.acc = P->acc;
+    st.cap_left = op.cap;
+    st.delivered = 0;
+    st.ncalls = 0;
+    st.win = 0;
+    st.win_base = 0;
+    st.win_valid = false;
+    scout_batch(st, ring, cap, op, batches[0], lane);
   }
   __syncthreads();
-  if (tid == 0) {
-    P->head = S.head;
-    P->moving_head = S.mh;
-    P->remain = S.remain;
-    P->acc = S.acc;
-    results[blockIdx.x].bytes = S.delivered;
-    results[blockIdx.x].calls = S.ncalls;
+
+  for (uint32_t b = 0;; b++) {
+    RecvBatch& cur = batches[b & 1];
+    const bool last = cur.last != 0;
+    if (warp == 0 && !last) scout_batch(st, ring, cap, op, batches[(b + 1) & 1], lane);
+    const uint32_t nframes = cur.nframes, nitems = cur.nitems;
+    while (true) {
+      uint32_t w = 0;
+      if (lane == 0) w = atomicAdd(&s_next[b & 1], 1u);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w >= nitems) break;
+      uint32_t fi = 0;
+      while (fi + 1 < nframes && cur.f[fi + 1].first_item <= w) fi++;
+      const RecvFrame fr = cur.f[fi];
+      const uint64_t c0 = (uint64_t)(w - fr.first_item) * kChunk;
+      uint64_t n = fr.n - c0;
+      const bool tail_item = n <= kChunk;
+      if (n > kChunk) n = kChunk;
+      // ---- scatter
+      const uint64_t pos = (fr.src_off + c0) & mask;
+      uint8_t* dst = op.dst + fr.dst_off + c0;
+      uint64_t seg1 = cap - pos;
+      if (seg1 > n) seg1 = n;
+      coop_copy<true>(dst, ring + pos, seg1, lane, 32);
+      if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, lane, 32);
+      __syncwarp();  // every lane's loads are done before any lane clears
+      // ---- clear-on-read: exactly what this item retired
+      uint64_t zs = pos, zl = n;
+      if (c0 == 0) {
+        zs = (pos + cap - fr.zhead) & mask;
+        zl += fr.zhead;
+      }
+      if (tail_item) zl += fr.ztail;
+      uint64_t z1 = cap - zs;
+      if (z1 > zl) z1 = zl;
+      coop_zero(ring + zs, z1, lane, 32);
+      if (zl > z1) coop_zero(ring, zl - z1, lane, 32);
+    }
+    const bool credit = cur.credit_flag != 0;
+    if (credit) __threadfence_system();  // the sender may reuse the space only once it reads as zero
+    __syncthreads();
+    if (tid == 0) {
+      s_next[b & 1] = 0;
+      if (credit) {
+        // updateStatus, pair.cc:624-641: 16-byte status_report to the peer
+        st_release_v2u64(P->peer_credit, cur.credit_val, 0);
+        if (P->peer_mirror) ((volatile PairMirror*)P->peer_mirror)->credit_head = cur.credit_val;
+      }
+    }
+    if (last) break;
+    // nobody may still be reading cur (= the buffer the scout fills next iteration) -- guaranteed
+    // by the barrier above; the scout's writes to the other buffer finished before it as well
+  }
+  if (tid == 0) {  // warp 0 lane 0 holds the final cursor
+    P->head = st.head;
+    P->moving_head = st.mh;
+    P->remain = st.remain;
+    P->acc = st.acc;
+    results[blockIdx.x].bytes = st.delivered;
+    results[blockIdx.x].calls = st.ncalls;
     uint32_t hm;
     uint64_t rd;
-    rx_probe(ring, cap, S.head, S.remain, hm, rd);
+    rx_probe(ring, cap, st.head, st.remain, hm, rd);
     publish_mirror(P->mirror, P, hm, rd);
   }
 }
