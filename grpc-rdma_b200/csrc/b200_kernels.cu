@@ -89,103 +89,121 @@ __device__ __forceinline__ uint4 ld_src16(const void* p) {
   return kRingSrc ? ld_ring16(p) : ld_stream16(p);
 }
 
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 8;  // 16-byte vectors in flight per lane: one 4 KiB work item = one block
 
-// dst 16-byte aligned, src misaligned by m = src & 15 (1..15): every output
-// vector is cut out of two aligned source vectors.  The second one always
-// contains a byte of the source range, so it never faults.
+__device__ __forceinline__ uint4 shfl_down1_wrap(uint4 a, uint4 next0, uint32_t lane) {
+  // lane L gets lane L+1's vector; lane 31 gets lane 0's vector of the next row
+  uint4 t, w;
+  t.x = __shfl_down_sync(0xffffffffu, a.x, 1);
+  t.y = __shfl_down_sync(0xffffffffu, a.y, 1);
+  t.z = __shfl_down_sync(0xffffffffu, a.z, 1);
+  t.w = __shfl_down_sync(0xffffffffu, a.w, 1);
+  w.x = __shfl_sync(0xffffffffu, next0.x, 0);
+  w.y = __shfl_sync(0xffffffffu, next0.y, 0);
+  w.z = __shfl_sync(0xffffffffu, next0.z, 0);
+  w.w = __shfl_sync(0xffffffffu, next0.w, 0);
+  return lane == 31 ? w : t;
+}
+
+// Warp-cooperative: dst 16-byte aligned, src misaligned by m = src & 15 (1..15).  Output vector i
+// is cut out of aligned source vectors i and i+1; vector i+1 is the neighbour lane's load (shuffle),
+// so every source byte is fetched once and kUnroll loads per lane are in flight.  Source vector
+// `nvec` always contains a byte of the range (never faults); vectors beyond it are not touched.
 template <bool kRingSrc, bool kHi, bool kShift>
 __device__ __noinline__ void copy_vec_shifted(uint8_t* dst, const uint8_t* src_al, uint64_t nvec, unsigned sh,
-                                              uint32_t tid, uint32_t nthr) {
+                                              uint32_t lane) {
   const uint4* s = reinterpret_cast<const uint4*>(src_al);
   uint4* d = reinterpret_cast<uint4*>(dst);
-  const uint64_t step = (uint64_t)nthr * kUnroll;
-  const uint64_t nfull = nvec / step * step;  // whole blocks: no predicates, kUnroll loads in flight
-  uint64_t base = tid;
-  for (; base < nfull; base += step) {
-    uint4 A[kUnroll], B[kUnroll];
+  const uint64_t step = 32ull * kUnroll;
+  const uint64_t nfull = nvec / step * step;
+  if (nfull) {
+    uint4 carry = ld_src16<kRingSrc>(s + lane);
+    for (uint64_t base = 0; base < nfull; base += step) {
+      uint4 A[kUnroll + 1];
+      A[0] = carry;
 #pragma unroll
-    for (int k = 0; k < kUnroll; k++) {
-      A[k] = ld_src16<kRingSrc>(s + base + (uint64_t)k * nthr);
-      B[k] = ld_src16<kRingSrc>(s + base + (uint64_t)k * nthr + 1);
+      for (int k = 1; k < kUnroll; k++) A[k] = ld_src16<kRingSrc>(s + base + 32ull * k + lane);
+      {
+        const uint64_t i = base + step + lane;  // next block's first row; only words <= nvec exist
+        A[kUnroll] = i <= nvec ? ld_src16<kRingSrc>(s + i) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; k++) {
+        const uint4 B = shfl_down1_wrap(A[k], A[k + 1], lane);
+        st_stream16(d + base + 32ull * k + lane, shift_window<kHi, kShift>(A[k], B, sh));
+      }
+      carry = A[kUnroll];
     }
-#pragma unroll
-    for (int k = 0; k < kUnroll; k++)
-      st_stream16(d + base + (uint64_t)k * nthr, shift_window<kHi, kShift>(A[k], B[k], sh));
   }
-  for (uint64_t i = nfull + tid; i < nvec; i += nthr) {
+  for (uint64_t i = nfull + lane; i < nvec; i += 32) {
     uint4 A = ld_src16<kRingSrc>(s + i), B = ld_src16<kRingSrc>(s + i + 1);
     st_stream16(d + i, shift_window<kHi, kShift>(A, B, sh));
   }
 }
 
 template <bool kRingSrc>
-__device__ __noinline__ void copy_vec_aligned(uint8_t* dst, const uint8_t* src, uint64_t nvec, uint32_t tid,
-                                              uint32_t nthr) {
+__device__ __noinline__ void copy_vec_aligned(uint8_t* dst, const uint8_t* src, uint64_t nvec, uint32_t lane) {
   const uint4* s = reinterpret_cast<const uint4*>(src);
   uint4* d = reinterpret_cast<uint4*>(dst);
-  const uint64_t step = (uint64_t)nthr * kUnroll;
+  const uint64_t step = 32ull * kUnroll;
   const uint64_t nfull = nvec / step * step;
-  uint64_t base = tid;
-  for (; base < nfull; base += step) {
+  for (uint64_t base = lane; base < nfull; base += step) {
     uint4 v[kUnroll];
 #pragma unroll
-    for (int k = 0; k < kUnroll; k++) v[k] = ld_src16<kRingSrc>(s + base + (uint64_t)k * nthr);
+    for (int k = 0; k < kUnroll; k++) v[k] = ld_src16<kRingSrc>(s + base + 32ull * k);
 #pragma unroll
-    for (int k = 0; k < kUnroll; k++) st_stream16(d + base + (uint64_t)k * nthr, v[k]);
+    for (int k = 0; k < kUnroll; k++) st_stream16(d + base + 32ull * k, v[k]);
   }
-  for (uint64_t i = nfull + tid; i < nvec; i += nthr) st_stream16(d + i, ld_src16<kRingSrc>(s + i));
+  for (uint64_t i = nfull + lane; i < nvec; i += 32) st_stream16(d + i, ld_src16<kRingSrc>(s + i));
 }
 
-// Cooperative copy of n bytes, any alignment on either side, by threads
-// tid in [0, nthr).  Bulk = aligned 16-byte stores; <16-byte head and tail use
-// one byte per thread.
+// Warp-cooperative copy of n bytes, any alignment on either side.  Bulk = aligned 16-byte
+// stores; the <16-byte head and tail use one byte per lane.
 template <bool kRingSrc>
-__device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint64_t n, uint32_t tid,
-                                          uint32_t nthr) {
+__device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint64_t n, uint32_t lane) {
   if (n == 0) return;
   uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
   if (head > n) head = n;
-  if (tid < head) dst[tid] = kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(src + tid) : src[tid];
+  if (lane < head) dst[lane] = kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(src + lane) : src[lane];
   dst += head;
   src += head;
   n -= head;
-  uint64_t nvec = n >> 4;
-  unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15);
+  const uint64_t nvec = n >> 4;
+  const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15);
   if (nvec) {
     if (m == 0) {
-      copy_vec_aligned<kRingSrc>(dst, src, nvec, tid, nthr);
+      copy_vec_aligned<kRingSrc>(dst, src, nvec, lane);
     } else {
       const uint8_t* sal = src - m;
-      unsigned sh = (m & 7) * 8;
+      const unsigned sh = (m & 7) * 8;
       if (m & 8) {
-        if (sh) copy_vec_shifted<kRingSrc, true, true>(dst, sal, nvec, sh, tid, nthr);
-        else copy_vec_shifted<kRingSrc, true, false>(dst, sal, nvec, sh, tid, nthr);
+        if (sh) copy_vec_shifted<kRingSrc, true, true>(dst, sal, nvec, sh, lane);
+        else copy_vec_shifted<kRingSrc, true, false>(dst, sal, nvec, sh, lane);
       } else {
-        copy_vec_shifted<kRingSrc, false, true>(dst, sal, nvec, sh, tid, nthr);
+        copy_vec_shifted<kRingSrc, false, true>(dst, sal, nvec, sh, lane);
       }
     }
   }
-  uint64_t done = nvec << 4;
-  uint64_t tail = n - done;
-  if (tid < tail)
-    dst[done + tid] = kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(src + done + tid) : src[done + tid];
+  const uint64_t done = nvec << 4;
+  const uint64_t tail = n - done;
+  if (lane < tail)
+    dst[done + lane] = kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(src + done + lane) : src[done + lane];
 }
 
-// Cooperative zero fill of n bytes at p (any alignment).
-__device__ __forceinline__ void coop_zero(uint8_t* p, uint64_t n, uint32_t tid, uint32_t nthr) {
+// Warp-cooperative zero fill of n bytes at p (any alignment).
+__device__ __forceinline__ void coop_zero(uint8_t* p, uint64_t n, uint32_t lane) {
   if (n == 0) return;
   uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
   if (head > n) head = n;
-  if (tid < head) p[tid] = 0;
+  if (lane < head) p[lane] = 0;
   p += head;
   n -= head;
-  uint64_t nvec = n >> 4;
+  const uint64_t nvec = n >> 4;
   uint4* d = reinterpret_cast<uint4*>(p);
   const uint4 z = make_uint4(0, 0, 0, 0);
-  for (uint64_t i = tid; i < nvec; i += nthr) st_stream16(d + i, z);
-  uint64_t done = nvec << 4;
-  if (tid < n - done) p[done + tid] = 0;
+  for (uint64_t i = lane; i < nvec; i += 32) st_stream16(d + i, z);
+  const uint64_t done = nvec << 4;
+  if (lane < n - done) p[done + lane] = 0;
 }
 
 // GetReadableSize / HasMessage of a pair whose cursor is (head, remain)
@@ -413,8 +431,8 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
       const uint64_t pos = (fd.off + 8 + c0) & mask;
       uint64_t seg1 = cap - pos;
       if (seg1 > n) seg1 = n;
-      coop_copy<false>(ring + pos, fd.src + c0, seg1, lane, 32);
-      if (n > seg1) coop_copy<false>(ring, fd.src + c0 + seg1, n - seg1, lane, 32);  // wrap: WR1 at remote+0
+      coop_copy<false>(ring + pos, fd.src + c0, seg1, lane);
+      if (n > seg1) coop_copy<false>(ring, fd.src + c0 + seg1, n - seg1, lane);  // wrap: WR1 at remote+0
     }
     if (sys_scope) __threadfence_system();
     else __threadfence();
@@ -646,8 +664,8 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
       uint8_t* dst = op.dst + fr.dst_off + c0;
       uint64_t seg1 = cap - pos;
       if (seg1 > n) seg1 = n;
-      coop_copy<true>(dst, ring + pos, seg1, lane, 32);
-      if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, lane, 32);
+      coop_copy<true>(dst, ring + pos, seg1, lane);
+      if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, lane);
       __syncwarp();  // every lane's loads are done before any lane clears
       // ---- clear-on-read: exactly what this item retired
       uint64_t zs = pos, zl = n;
@@ -658,8 +676,8 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
       if (tail_item) zl += fr.ztail;
       uint64_t z1 = cap - zs;
       if (z1 > zl) z1 = zl;
-      coop_zero(ring + zs, z1, lane, 32);
-      if (zl > z1) coop_zero(ring, zl - z1, lane, 32);
+      coop_zero(ring + zs, z1, lane);
+      if (zl > z1) coop_zero(ring, zl - z1, lane);
     }
     const bool credit = cur.credit_flag != 0;
     if (credit) __threadfence_system();  // the sender may reuse the space only once it reads as zero
