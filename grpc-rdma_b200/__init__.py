@@ -103,6 +103,8 @@ _SIGS = {
     "b200_batch_results": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "b200_batch_calls": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "b200_batch_destroy": (None, [C.c_void_p]),
+    "b200_probe_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint32,
+                                  C.c_uint32, C.c_uint32, C.c_void_p]),
     "b200_launch_count": (C.c_uint64, []),
 }
 

@@ -123,4 +123,7 @@ void launch_recv(PairDev* pairs, const RecvOpDev* ops, OpResult* results, int no
 void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, uint32_t* ready_count,
                       int32_t* ready_slots, int n, void* stream);
 
+void launch_probe_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,
+                       int threads, uint32_t mis, uint32_t item_bytes, uint32_t dynamic, void* stream);
+
 }  // namespace b200

@@ -244,126 +244,227 @@ __device__ __forceinline__ void publish_mirror(PairMirror* m, const PairDev* P, 
 }
 
 // =========================================================================
-// k_send
+// Producer / consumer skeleton shared by k_send and k_recv
 // =========================================================================
 //
-// One CTA per (pair, write).  Warp 0 plans Send() call j+1 (credit snapshot,
-// warp scan of encoded sizes, cut detection) while all warps -- warp 0 joins
-// once the plan is published -- move the bytes of call j in 4 KiB work items
-// claimed from a shared counter.  One CTA barrier per call; footers of call j
-// are written after that barrier (everything else of the call is fenced before).
+// One CTA per (pair, op).  Warp 0 is the producer: it runs the reference's
+// integer logic (Send planning / frame-list walking) ahead of the data movers
+// and publishes 4 KiB work items into a ticket ring in shared memory.  All
+// other warps (and warp 0 once it has nothing left to publish) claim items from
+// a shared counter and move bytes.  There is no CTA barrier on the steady-state
+// path; a "segment" ends only where the protocol needs everything before it to
+// be finished: the footer flush of Send, the credit write of Recv, the end of
+// the op.
 
-constexpr int kSendThreads = 512;
+constexpr int kThreads = 512;
 constexpr uint32_t kChunk = 4096;  // payload bytes per work item
+constexpr uint32_t kQI = 256;      // ticket ring entries (1 MiB of look-ahead)
 
-struct FrameDesc {
-  const uint8_t* src;
-  uint64_t len;   // payload bytes
-  uint64_t off;   // ring offset of the frame header
-  uint32_t first_item;
-  uint32_t _pad;
+struct WorkItem {      // 32 bytes
+  uint64_t a;          // send: source pointer          recv: ring offset of the payload bytes
+  uint64_t b;          // send: ring offset (payload)   recv: offset in the destination
+  uint64_t c;          // send: header value (chunk 0)  recv: zhead | ztail << 16
+  uint32_t n;          // bytes
+  uint32_t ready;      // ticket: item id + 1 when published, 0 when free
 };
 
-struct SendCall {
-  FrameDesc frames[kMaxSgeLimit];
-  uint32_t nframes, nitems, last, _pad;
+struct PipeCtl {
+  uint32_t next;         // next item id to claim
+  uint32_t total_items;  // valid once seg_done
+  uint32_t seg_done;
+  uint32_t op_done;
 };
 
-struct SendPlanState {  // touched by warp 0 only
+__device__ __forceinline__ uint32_t ld_shared_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+
+// producer side: wait for the slot of item `id`, fill it, publish
+__device__ __forceinline__ void publish_item(WorkItem* q, uint32_t id, uint64_t a, uint64_t b, uint64_t c,
+                                             uint32_t n) {
+  WorkItem* slot = &q[id % kQI];
+  while (ld_shared_volatile(&slot->ready) != 0) __nanosleep(20);
+  slot->a = a;
+  slot->b = b;
+  slot->c = c;
+  slot->n = n;
+  __threadfence_block();
+  *(volatile uint32_t*)&slot->ready = id + 1;
+}
+
+// consumer side: claim the next item; false when the segment is drained
+__device__ __forceinline__ bool claim_item(WorkItem* q, PipeCtl* ctl, uint32_t lane, uint64_t& a, uint64_t& b,
+                                           uint64_t& c, uint32_t& n) {
+  uint32_t w = 0;
+  if (lane == 0) w = atomicAdd(&ctl->next, 1u);
+  w = __shfl_sync(0xffffffffu, w, 0);
+  WorkItem* slot = &q[w % kQI];
+  bool got = false;
+  while (true) {
+    if (ld_shared_volatile(&slot->ready) == w + 1) {
+      got = true;
+      break;
+    }
+    if (ld_shared_volatile(&ctl->seg_done) && w >= ld_shared_volatile(&ctl->total_items)) {
+      // re-check: the item may have been published between the two reads
+      got = ld_shared_volatile(&slot->ready) == w + 1;
+      break;
+    }
+    __nanosleep(40);
+  }
+  got = __any_sync(0xffffffffu, got);
+  if (!got) return false;
+  __threadfence_block();
+  a = slot->a;
+  b = slot->b;
+  c = slot->c;
+  n = slot->n;
+  __syncwarp();
+  if (lane == 0) *(volatile uint32_t*)&slot->ready = 0;  // slot may be refilled
+  return true;
+}
+
+// =========================================================================
+// k_send
+// =========================================================================
+
+constexpr uint32_t kFootCap = 2048;  // footers buffered per segment (ring offsets / 8)
+
+struct SendPlanState {  // producer-only
   uint64_t rt, cap, staging, total_left, written_total, ncalls, cur, bidx;
   uint32_t partial, max_sge;
 };
 
-// One PairPollable::Send call (pair.cc:645-734) as integer planning; executed by
-// warp 0, all lanes converged.  Returns true when this was the last call.
-__device__ __forceinline__ void plan_send_call(const SendOpDev& op, const PairDev* P, SendPlanState& S,
-                                               SendCall& out, uint32_t lane) {
-  const uint64_t cap = S.cap, mask = cap - 1, rt = S.rt;
-  const uint64_t rh = ld_acquire_u64(&P->credit_head);  // credit snapshot, once per call (pair.cc:650)
-  const uint64_t cur = S.cur, bidx = S.bidx;
-  const uint64_t idx = cur + lane;
-  const bool valid = lane < S.max_sge && idx < op.nslices;
-  const uint8_t* ptr = nullptr;
-  uint64_t len = 0;
-  if (valid) {
-    SliceDev sl = op.slices[idx];
-    uint64_t skip = lane == 0 ? bidx : 0;
-    ptr = sl.ptr + skip;
-    len = sl.len - skip;
+struct SendCallScratch {  // frames of the call being published
+  const uint8_t* src[kMaxSgeLimit];
+  uint64_t len[kMaxSgeLimit];
+  uint64_t off[kMaxSgeLimit];
+  uint32_t first_item[kMaxSgeLimit + 1];
+};
+
+// Producer: plan PairPollable::Send calls (pair.cc:645-734) one after another and publish
+// their frames as work items until the op is finished or the footer buffer is full.
+__device__ __noinline__ void send_produce_segment(const SendOpDev& op, const PairDev* P, SendPlanState& S,
+                                                  SendCallScratch& CS, WorkItem* q, PipeCtl* ctl, uint32_t* foot8,
+                                                  uint32_t* nfoot_out, uint32_t lane) {
+  const uint64_t cap = S.cap, mask = cap - 1;
+  uint32_t base_item = 0, nfoot = 0;
+  bool op_done = false;
+  while (nfoot + kMaxSgeLimit <= kFootCap) {
+    const uint64_t rt = S.rt;
+    const uint64_t rh = ld_acquire_u64(&P->credit_head);  // credit snapshot, once per call (pair.cc:650)
+    const uint64_t cur = S.cur, bidx = S.bidx;
+    const uint64_t idx = cur + lane;
+    const bool valid = lane < S.max_sge && idx < op.nslices;
+    const uint8_t* ptr = nullptr;
+    uint64_t len = 0;
+    if (valid) {
+      SliceDev sl = op.slices[idx];
+      const uint64_t skip = lane == 0 ? bidx : 0;
+      ptr = sl.ptr + skip;
+      len = sl.len - skip;
+    }
+    const uint64_t e = valid ? encoded_size(len) : 0;
+    uint64_t incl = e;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint64_t a = incl - e;  // staging / ring bytes consumed before this slice
+    // min(CWS(send_buf_free), CWS(recv_buf_free)) (pair.cc:676-681): both shrink by `a`
+    const uint64_t fr = free_size(cap, rh, rt);
+    const uint64_t lim = S.staging < fr ? S.staging : fr;
+    const uint64_t room = calc_writable(lim > a ? lim - a : 0);
+    const bool fits = valid && len != 0 && len <= room;
+    const unsigned bad = __ballot_sync(0xffffffffu, !fits);
+    const int first_bad = __ffs(bad) - 1;
+    const int nfull = first_bad < 0 ? 32 : first_bad;
+    uint64_t p = 0;
+    if ((int)lane < nfull) p = len;
+    else if ((int)lane == nfull && valid && len != 0) p = room;  // cut: space ran out
+    const unsigned fmask = __ballot_sync(0xffffffffu, p != 0);
+    const uint32_t nframes = __popc(fmask);  // frames are lanes 0..nframes-1
+    uint64_t wsum = p, esum = p ? encoded_size(p) : 0;
+    const uint32_t items = p ? (uint32_t)((p + kChunk - 1) / kChunk) : 0;
+    uint32_t items_incl = items;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, items_incl, o);
+      if (lane >= (uint32_t)o) items_incl += t;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+      esum += __shfl_xor_sync(0xffffffffu, esum, o);
+    }
+    const uint32_t nitems = __shfl_sync(0xffffffffu, items_incl, 31);
+    const uint64_t cut_p = __shfl_sync(0xffffffffu, p, nfull < 32 ? nfull : 0);
+    const uint64_t foff = (rt + a) & mask;
+    CS.first_item[lane] = items_incl - items;
+    if (p) {
+      CS.src[lane] = ptr;
+      CS.len[lane] = p;
+      CS.off[lane] = foff;
+      foot8[nfoot + lane] = (uint32_t)(((foff + 8 + round_up8(p)) & mask) >> 3);
+    }
+    if (lane == 0) {
+      CS.first_item[32] = nitems;
+      S.rt = (rt + esum) & mask;
+      S.partial = wsum < S.total_left;  // pair.cc:712
+      S.total_left -= wsum;
+      S.written_total += wsum;
+      if (wsum) S.ncalls++;
+      // cursor advance (rdma_flush, rdma_bp_posix.cc:480-493)
+      uint64_t nb = 0;
+      if (nfull < 32 && nframes > (uint32_t)nfull) nb = (nfull == 0 ? bidx : 0) + cut_p;  // cut slice stays current
+      else if (nfull == 0) nb = bidx;                                                    // nothing consumed
+      S.cur = cur + nfull;
+      S.bidx = nb;
+    }
+    __syncwarp();
+    nfoot += nframes;
+    // publish this call's items in id order, 32 at a time
+    for (uint32_t it = lane; it < nitems; it += 32) {
+      uint32_t f = 0;
+      while (f + 1 < nframes && CS.first_item[f + 1] <= it) f++;
+      const uint64_t c0 = (uint64_t)(it - CS.first_item[f]) * kChunk;
+      const uint64_t flen = CS.len[f];
+      uint64_t n = flen - c0;
+      if (n > kChunk) n = kChunk;
+      publish_item(q, base_item + it, reinterpret_cast<uint64_t>(CS.src[f] + c0), (CS.off[f] + 8 + c0) & mask,
+                   c0 == 0 ? flen : 0, (uint32_t)n);
+    }
+    __syncwarp();
+    base_item += nitems;
+    const bool last = (wsum == 0) || !(op.flags & kFlagUntilBlocked) || S.total_left == 0;
+    if (last) {
+      op_done = true;
+      break;
+    }
   }
-  const uint64_t e = valid ? encoded_size(len) : 0;
-  uint64_t incl = e;
-  for (int o = 1; o < 32; o <<= 1) {
-    uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= (uint32_t)o) incl += t;
-  }
-  const uint64_t a = incl - e;  // staging / ring bytes consumed before this slice
-  // min(CWS(send_buf_free), CWS(recv_buf_free)) (pair.cc:676-681): both shrink by `a`
-  const uint64_t fr = free_size(cap, rh, rt);
-  const uint64_t lim = S.staging < fr ? S.staging : fr;
-  const uint64_t room = calc_writable(lim > a ? lim - a : 0);
-  const bool fits = valid && len != 0 && len <= room;
-  const unsigned bad = __ballot_sync(0xffffffffu, !fits);
-  const int first_bad = __ffs(bad) - 1;
-  const int nfull = first_bad < 0 ? 32 : first_bad;
-  uint64_t p = 0;
-  if ((int)lane < nfull) p = len;
-  else if ((int)lane == nfull && valid && len != 0) p = room;  // cut: space ran out
-  const unsigned fmask = __ballot_sync(0xffffffffu, p != 0);
-  const uint32_t nframes = __popc(fmask);
-  uint64_t wsum = p, esum = p ? encoded_size(p) : 0;
-  const uint32_t items = p ? (uint32_t)((p + kChunk - 1) / kChunk) : 0;
-  uint32_t items_incl = items;
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, items_incl, o);
-    if (lane >= (uint32_t)o) items_incl += t;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-    esum += __shfl_xor_sync(0xffffffffu, esum, o);
-  }
-  if (p) {
-    FrameDesc& f = out.frames[lane];  // frames are lanes 0..nframes-1
-    f.src = ptr;
-    f.len = p;
-    f.off = (rt + a) & mask;
-    f.first_item = items_incl - items;
-  }
-  const uint32_t nitems = __shfl_sync(0xffffffffu, items_incl, 31);
-  const uint64_t cut_p = __shfl_sync(0xffffffffu, p, nfull < 32 ? nfull : 0);
   if (lane == 0) {
-    out.nframes = nframes;
-    out.nitems = nitems;
-    S.rt = (rt + esum) & mask;
-    S.partial = wsum < S.total_left;  // pair.cc:712
-    S.total_left -= wsum;
-    S.written_total += wsum;
-    if (wsum) S.ncalls++;
-    // cursor advance (rdma_flush, rdma_bp_posix.cc:480-493)
-    uint64_t nb = 0;
-    if (nfull < 32 && nframes > (uint32_t)nfull) nb = (nfull == 0 ? bidx : 0) + cut_p;  // cut slice stays current
-    else if (nfull == 0) nb = bidx;                                                    // nothing consumed
-    S.cur = cur + nfull;
-    S.bidx = nb;
-    out.last = (wsum == 0) || !(op.flags & kFlagUntilBlocked) || S.total_left == 0;
+    *nfoot_out = nfoot;
+    ctl->total_items = base_item;
+    ctl->op_done = op_done ? 1u : 0u;
+    __threadfence_block();
+    *(volatile uint32_t*)&ctl->seg_done = 1;
   }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kSendThreads, 2)
+__global__ void __launch_bounds__(kThreads, 2)
 k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult* __restrict__ results) {
-  __shared__ SendCall calls[2];
+  __shared__ WorkItem q[kQI];
+  __shared__ PipeCtl ctl;
   __shared__ SendPlanState PS;
+  __shared__ SendCallScratch CS;
+  __shared__ uint32_t foot8[kFootCap];
+  __shared__ uint32_t s_nfoot;
   __shared__ unsigned long long s_total;
-  __shared__ uint32_t s_next[2];
   __shared__ uint32_t s_status;
   const SendOpDev op = ops[blockIdx.x];
   PairDev* P = &pairs[op.slot];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  if (tid < kQI) q[tid].ready = 0;
   if (tid == 0) {
     s_total = 0;
-    s_next[0] = s_next[1] = 0;
     s_status = P->status;
     PS.rt = P->remote_tail;
     PS.cap = P->cap;
@@ -378,7 +479,7 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
   __syncthreads();
   {  // total_slice_size, pair.cc:661-664
     unsigned long long part = 0;
-    for (uint64_t i = tid; i < op.nslices; i += kSendThreads) part += op.slices[i].len;
+    for (uint64_t i = tid; i < op.nslices; i += kThreads) part += op.slices[i].len;
     for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
     if (lane == 0 && part) atomicAdd(&s_total, part);
   }
@@ -391,62 +492,43 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
     return;
   }
   if (tid == 0) PS.total_left = s_total - op.byte_idx;
-  __syncthreads();
-  const uint64_t cap = PS.cap, mask = cap - 1;
+  const uint64_t cap = P->cap, mask = cap - 1;
   uint8_t* ring = P->peer_ring;
   const bool sys_scope = P->wire != 0;
 
-  if (warp == 0) plan_send_call(op, P, PS, calls[0], lane);
-  __syncthreads();
-
-  for (uint32_t j = 0;; j++) {
-    SendCall& cur = calls[j & 1];
-    const bool last = cur.last != 0;
-    // footers of the previous call: everything else of it was fenced before the barrier.
-    // A frame is complete for the reader only when header != 0 and footer == ~0
-    // (ring_buffer.cc:75-96), so the footer goes last.
-    if (j > 0) {
-      const SendCall& prev = calls[(j - 1) & 1];
-      if (tid >= 32 && tid - 32 < prev.nframes) {
-        const FrameDesc fd = prev.frames[tid - 32];
-        *reinterpret_cast<uint64_t*>(ring + ((fd.off + 8 + round_up8(fd.len)) & mask)) = kFooter;
-      }
+  while (true) {
+    if (tid == 0) {
+      ctl.next = 0;
+      ctl.total_items = 0;
+      ctl.seg_done = 0;
+      ctl.op_done = 0;
+      s_nfoot = 0;
     }
-    __syncthreads();  // prev.frames fully consumed before warp 0 overwrites that buffer
-    if (warp == 0 && !last) plan_send_call(op, P, PS, calls[(j + 1) & 1], lane);
-    // ---------------------------------------------- move the bytes of call j
-    const uint32_t nframes = cur.nframes, nitems = cur.nitems;
-    while (true) {
-      uint32_t w = 0;
-      if (lane == 0) w = atomicAdd(&s_next[j & 1], 1u);
-      w = __shfl_sync(0xffffffffu, w, 0);
-      if (w >= nitems) break;
-      uint32_t f = 0;
-      while (f + 1 < nframes && cur.frames[f + 1].first_item <= w) f++;
-      const FrameDesc fd = cur.frames[f];
-      const uint64_t c0 = (uint64_t)(w - fd.first_item) * kChunk;
-      uint64_t n = fd.len - c0;
-      if (n > kChunk) n = kChunk;
-      if (c0 == 0 && lane == 0) *reinterpret_cast<uint64_t*>(ring + fd.off) = fd.len;  // AppendHeader
-      const uint64_t pos = (fd.off + 8 + c0) & mask;
-      uint64_t seg1 = cap - pos;
+    __syncthreads();
+    if (warp == 0) send_produce_segment(op, P, PS, CS, q, &ctl, foot8, &s_nfoot, lane);
+    // ---------------------------------------------- move bytes
+    uint64_t a, b, c;
+    uint32_t n;
+    while (claim_item(q, &ctl, lane, a, b, c, n)) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a);
+      if (c != 0 && lane == 0) *reinterpret_cast<uint64_t*>(ring + ((b + cap - 8) & mask)) = c;  // AppendHeader
+      uint64_t seg1 = cap - b;
       if (seg1 > n) seg1 = n;
-      coop_copy<false>(ring + pos, fd.src + c0, seg1, lane);
-      if (n > seg1) coop_copy<false>(ring, fd.src + c0 + seg1, n - seg1, lane);  // wrap: WR1 at remote+0
+      coop_copy<false>(ring + b, src, seg1, lane);
+      if (n > seg1) coop_copy<false>(ring, src + seg1, n - seg1, lane);  // wrap: WR1 at remote+0
     }
+    // footers last: a frame is complete for the reader only when header != 0 and footer == ~0
+    // (ring_buffer.cc:75-96), so everything else of the segment is made visible first
     if (sys_scope) __threadfence_system();
     else __threadfence();
     __syncthreads();
-    if (tid == 0) s_next[j & 1] = 0;
-    if (last) {
-      if (tid < nframes) {
-        const FrameDesc fd = cur.frames[tid];
-        *reinterpret_cast<uint64_t*>(ring + ((fd.off + 8 + round_up8(fd.len)) & mask)) = kFooter;
-      }
-      break;
-    }
+    const uint32_t nfoot = s_nfoot;
+    for (uint32_t i = tid; i < nfoot; i += kThreads)
+      *reinterpret_cast<uint64_t*>(ring + ((uint64_t)foot8[i] << 3)) = kFooter;
+    const bool done = ctl.op_done != 0;
+    __syncthreads();
+    if (done) break;
   }
-  __syncthreads();
   if (tid == 0) {
     P->remote_tail = PS.rt;
     P->partial_write = PS.partial;
@@ -476,40 +558,19 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
 // k_recv
 // =========================================================================
 //
-// One CTA per (pair, read).  The frames of a ring form a linked list (the next
-// header sits right after the previous footer), so warp 0 is a scout: it walks
-// the list through a 256-byte register window (one 8-byte word per lane, so a
-// 9-byte HTTP/2 header frame and the header of the payload frame behind it cost
-// a single trip to memory), applies the Read/Recv integer logic and queues
-// batches of frames.  While the scout walks batch b+1, all warps scatter batch b
-// in 4 KiB work items: load, store to the destination slice, __syncwarp, then
-// clear exactly the ring bytes this warp just read (clear-on-read is part of
-// the wire protocol, ring_buffer.cc:146,160,180).  One CTA barrier per batch.
+// The frames of a ring form a linked list (the next header sits right after the
+// previous footer), so the producer is a scout: it walks the list through a
+// 256-byte register window (one 8-byte word per lane: a 9-byte HTTP/2 header
+// frame and the header of the payload frame behind it cost a single trip to
+// memory), applies the Read/Recv integer logic and publishes 4 KiB items.
+// Consumers: load, store to the destination slice, __syncwarp, then clear
+// exactly the ring bytes just read (clear-on-read is part of the wire protocol,
+// ring_buffer.cc:146,160,180).  A segment ends at a credit point or at the end.
 
-constexpr int kRecvThreads = 512;
-constexpr int kBatchFrames = 32;
-constexpr uint64_t kBatchBytes = 192 * 1024;  // close a batch once this much payload is queued
-
-struct RecvFrame {
-  uint64_t src_off;   // ring offset of the first payload byte to deliver
-  uint64_t n;         // bytes to deliver
-  uint64_t dst_off;   // offset in the destination
-  uint32_t zhead;     // bytes to clear before the payload (the header word on first touch)
-  uint32_t ztail;     // bytes to clear after it (pad + footer once the frame is finished)
-  uint32_t first_item;
-  uint32_t _pad;
-};
-
-struct RecvBatch {
-  RecvFrame f[kBatchFrames];
-  uint64_t credit_val;
-  uint32_t nframes, nitems, credit_flag, last;
-};
-
-struct ScoutState {  // registers of warp 0, uniform across lanes
+struct ScoutState {  // producer-only, lives in shared memory between segments
   uint64_t head, mh, remain, acc, cap_left, delivered, ncalls;
-  uint64_t win, win_base;
-  bool win_valid;
+  uint64_t credit_val;
+  uint32_t credit_flag;
 };
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const void* p) {
@@ -518,102 +579,132 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const void* p) {
   return v;
 }
 
-// 8-byte word at ring offset `off` through the scout's window
-__device__ __forceinline__ uint64_t scout_peek(ScoutState& st, const uint8_t* ring, uint64_t mask, uint64_t off,
-                                               uint32_t lane) {
-  uint64_t d = (off - st.win_base) & mask;
-  if (!st.win_valid || d >= 256) {
-    st.win_base = off;
-    st.win = ld_volatile_u64(ring + ((off + 8ull * lane) & mask));
-    st.win_valid = true;
-    d = 0;
-  }
-  return __shfl_sync(0xffffffffu, st.win, (int)(d >> 3));
-}
-
-// Queue the next batch: RingBufferPollable::Read (ring_buffer.cc:122-191) + PairPollable::Recv's
-// credit rule (pair.cc:276-284) as integer logic over the frame list.
-__device__ __forceinline__ void scout_batch(ScoutState& st, const uint8_t* ring, uint64_t cap, const RecvOpDev& op,
-                                            RecvBatch& out, uint32_t lane) {
+// Producer: RingBufferPollable::Read (ring_buffer.cc:122-191) + PairPollable::Recv's credit
+// rule (pair.cc:276-284) as integer logic over the frame list.
+__device__ __noinline__ void recv_produce_segment(const RecvOpDev& op, const uint8_t* ring, uint64_t cap,
+                                                  ScoutState& SS, WorkItem* q, PipeCtl* ctl, uint32_t lane) {
   const uint64_t mask = cap - 1;
-  uint32_t nframes = 0, nitems = 0, credit = 0, last = 0;
-  uint64_t bytes = 0, credit_val = 0;
-  while (nframes < (uint32_t)kBatchFrames && bytes < kBatchBytes) {
+  uint64_t head = SS.head, mh = SS.mh, remain = SS.remain, acc = SS.acc, cap_left = SS.cap_left;
+  uint64_t delivered = SS.delivered, ncalls = SS.ncalls;
+  uint64_t win = 0, win_base = 0;
+  bool win_valid = false;
+  uint32_t base_item = 0, credit = 0, last = 0;
+  uint64_t credit_val = 0;
+  uint64_t last_reload = 0;
+  bool have_last = false;
+  auto peek = [&](uint64_t off) -> uint64_t {  // 8-byte ring word at `off` through the window
+    uint64_t d = (off - win_base) & mask;
+    if (!win_valid || d >= 256) {
+      // Frame lists are usually periodic (chttp2: 9-byte header frame + 16 KiB payload frame), so
+      // the distance between the last two window reloads predicts where the next ones will be:
+      // pull those lines into L2 now, 16 hops ahead, so the list walk is not one DRAM trip per hop.
+      if (have_last) {
+        const uint64_t stride = (off - last_reload) & mask;
+        if (stride >= 256) {
+          const uint64_t pf = (off + (uint64_t)((lane & 15) + 1) * stride + (lane >> 4) * 128) & mask;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ring + pf));
+        }
+      }
+      last_reload = off;
+      have_last = true;
+      win_base = off;
+      win = ld_volatile_u64(ring + ((off + 8ull * lane) & mask));
+      win_valid = true;
+      d = 0;
+    }
+    return __shfl_sync(0xffffffffu, win, (int)(d >> 3));
+  };
+  while (true) {
     uint64_t r;
     bool opening = false;
-    if (st.remain > 0) {
-      r = st.remain;
+    if (remain > 0) {
+      r = remain;
     } else {  // GetReadableSize, ring_buffer.cc:67-97
-      const uint64_t hdr = scout_peek(st, ring, mask, st.head, lane);
+      const uint64_t hdr = peek(head);
       if (hdr == 0 || hdr > cap - kReserved) { last = 1; break; }
-      const uint64_t foot = scout_peek(st, ring, mask, (st.head + 8 + round_up8(hdr)) & mask, lane);
+      const uint64_t foot = peek((head + 8 + round_up8(hdr)) & mask);
       if (foot != kFooter) { last = 1; break; }
       r = hdr;
       opening = true;
     }
-    const uint64_t n = r < st.cap_left ? r : st.cap_left;
+    const uint64_t n = r < cap_left ? r : cap_left;
     if (n == 0) { last = 1; break; }
     if (opening) {  // first touch of this frame, ring_buffer.cc:135-147
-      st.mh = (st.head + 8) & mask;
-      st.head = (st.head + 16 + round_up8(r)) & mask;
+      mh = (head + 8) & mask;
+      head = (head + 16 + round_up8(r)) & mask;
     }
-    const uint64_t src_off = st.mh;
-    st.mh = (st.mh + n) & mask;
-    st.remain = r - n;
+    const uint64_t src_off = mh;
+    mh = (mh + n) & mask;
+    remain = r - n;
     uint32_t ztail = 0;
-    if (st.remain == 0) {  // pad + footer, ring_buffer.cc:170-183
-      const uint64_t up = round_up8(st.mh);
-      ztail = (uint32_t)(up - st.mh) + 8;
-      st.mh = ((up & mask) + 8) & mask;
+    if (remain == 0) {  // pad + footer, ring_buffer.cc:170-183
+      const uint64_t up = round_up8(mh);
+      ztail = (uint32_t)(up - mh) + 8;
+      mh = ((up & mask) + 8) & mask;
     }
     const uint32_t zhead = opening ? 8u : 0u;
     const uint32_t items = (uint32_t)((n + kChunk - 1) / kChunk);
-    if (lane == 0) {
-      RecvFrame& f = out.f[nframes];
-      f.src_off = src_off;
-      f.n = n;
-      f.dst_off = st.delivered;
-      f.zhead = zhead;
-      f.ztail = ztail;
-      f.first_item = nitems;
+    for (uint32_t ci = lane; ci < items; ci += 32) {
+      const uint64_t c0 = (uint64_t)ci * kChunk;
+      uint64_t m = n - c0;
+      const bool tail_item = m <= kChunk;
+      if (m > kChunk) m = kChunk;
+      const uint64_t z = (ci == 0 ? zhead : 0u) | ((uint64_t)(tail_item ? ztail : 0u) << 16);
+      publish_item(q, base_item + ci, (src_off + c0) & mask, delivered + c0, z, (uint32_t)m);
     }
-    nframes++;
-    nitems += items;
-    bytes += n;
-    st.delivered += n;
-    st.cap_left -= n;
-    st.ncalls++;
-    st.acc += (uint64_t)zhead + n + ztail;  // internal_bytes_read of this call
-    if (st.acc >= cap / 2) {                // pair.cc:276-284: credit goes out after this batch is cleared
+    __syncwarp();
+    base_item += items;
+    delivered += n;
+    cap_left -= n;
+    ncalls++;
+    acc += (uint64_t)zhead + n + ztail;  // internal_bytes_read of this call
+    if (acc >= cap / 2) {                // pair.cc:276-284: credit goes out once all of this is cleared
       credit = 1;
-      credit_val = st.mh;
-      st.acc = 0;
+      credit_val = mh;
+      acc = 0;
     }
-    if (!(op.flags & kFlagUntilBlocked) || st.cap_left == 0) { last = 1; break; }
+    if (!(op.flags & kFlagUntilBlocked) || cap_left == 0) { last = 1; break; }
     if (credit) break;
   }
   if (lane == 0) {
-    out.nframes = nframes;
-    out.nitems = nitems;
-    out.credit_flag = credit;
-    out.credit_val = credit_val;
-    out.last = last;
+    SS.head = head;
+    SS.mh = mh;
+    SS.remain = remain;
+    SS.acc = acc;
+    SS.cap_left = cap_left;
+    SS.delivered = delivered;
+    SS.ncalls = ncalls;
+    SS.credit_flag = credit;
+    SS.credit_val = credit_val;
+    ctl->total_items = base_item;
+    ctl->op_done = last;
+    __threadfence_block();
+    *(volatile uint32_t*)&ctl->seg_done = 1;
   }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kRecvThreads, 2)
+__global__ void __launch_bounds__(kThreads, 2)
 k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult* __restrict__ results) {
-  __shared__ RecvBatch batches[2];
-  __shared__ uint32_t s_next[2];
+  __shared__ WorkItem q[kQI];
+  __shared__ PipeCtl ctl;
+  __shared__ ScoutState SS;
   __shared__ uint32_t s_status;
   const RecvOpDev op = ops[blockIdx.x];
   PairDev* P = &pairs[op.slot];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  if (tid < kQI) q[tid].ready = 0;
   if (tid == 0) {
     s_status = P->status;
-    s_next[0] = s_next[1] = 0;
+    SS.head = P->head;
+    SS.mh = P->moving_head;
+    SS.remain = P->remain;
+    SS.acc = P->acc;
+    SS.cap_left = op.cap;
+    SS.delivered = 0;
+    SS.ncalls = 0;
+    SS.credit_flag = 0;
   }
   __syncthreads();
   if (s_status != kStConnected) {  // pair.cc:266-268
@@ -626,84 +717,57 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
   uint8_t* ring = P->ring;
   const uint64_t cap = P->cap, mask = cap - 1;
 
-  ScoutState st;
-  if (warp == 0) {
-    st.head = P->head;
-    st.mh = P->moving_head;
-    st.remain = P->remain;
-    st.acc = P->acc;
-    st.cap_left = op.cap;
-    st.delivered = 0;
-    st.ncalls = 0;
-    st.win = 0;
-    st.win_base = 0;
-    st.win_valid = false;
-    scout_batch(st, ring, cap, op, batches[0], lane);
-  }
-  __syncthreads();
-
-  for (uint32_t b = 0;; b++) {
-    RecvBatch& cur = batches[b & 1];
-    const bool last = cur.last != 0;
-    if (warp == 0 && !last) scout_batch(st, ring, cap, op, batches[(b + 1) & 1], lane);
-    const uint32_t nframes = cur.nframes, nitems = cur.nitems;
-    while (true) {
-      uint32_t w = 0;
-      if (lane == 0) w = atomicAdd(&s_next[b & 1], 1u);
-      w = __shfl_sync(0xffffffffu, w, 0);
-      if (w >= nitems) break;
-      uint32_t fi = 0;
-      while (fi + 1 < nframes && cur.f[fi + 1].first_item <= w) fi++;
-      const RecvFrame fr = cur.f[fi];
-      const uint64_t c0 = (uint64_t)(w - fr.first_item) * kChunk;
-      uint64_t n = fr.n - c0;
-      const bool tail_item = n <= kChunk;
-      if (n > kChunk) n = kChunk;
+  while (true) {
+    if (tid == 0) {
+      ctl.next = 0;
+      ctl.total_items = 0;
+      ctl.seg_done = 0;
+      ctl.op_done = 0;
+    }
+    __syncthreads();
+    if (warp == 0) recv_produce_segment(op, ring, cap, SS, q, &ctl, lane);
+    uint64_t a, b, c;
+    uint32_t n;
+    while (claim_item(q, &ctl, lane, a, b, c, n)) {
       // ---- scatter
-      const uint64_t pos = (fr.src_off + c0) & mask;
-      uint8_t* dst = op.dst + fr.dst_off + c0;
-      uint64_t seg1 = cap - pos;
+      uint8_t* dst = op.dst + b;
+      uint64_t seg1 = cap - a;
       if (seg1 > n) seg1 = n;
-      coop_copy<true>(dst, ring + pos, seg1, lane);
+      coop_copy<true>(dst, ring + a, seg1, lane);
       if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, lane);
       __syncwarp();  // every lane's loads are done before any lane clears
       // ---- clear-on-read: exactly what this item retired
-      uint64_t zs = pos, zl = n;
-      if (c0 == 0) {
-        zs = (pos + cap - fr.zhead) & mask;
-        zl += fr.zhead;
-      }
-      if (tail_item) zl += fr.ztail;
+      const uint32_t zhead = (uint32_t)(c & 0xffff), ztail = (uint32_t)(c >> 16);
+      const uint64_t zs = (a + cap - zhead) & mask;
+      const uint64_t zl = (uint64_t)zhead + n + ztail;
       uint64_t z1 = cap - zs;
       if (z1 > zl) z1 = zl;
       coop_zero(ring + zs, z1, lane);
       if (zl > z1) coop_zero(ring, zl - z1, lane);
     }
-    const bool credit = cur.credit_flag != 0;
-    if (credit) __threadfence_system();  // the sender may reuse the space only once it reads as zero
+    const bool credit = ld_shared_volatile(&SS.credit_flag) != 0;  // stable: the producer finished this segment
+    if (credit) __threadfence_system();       // the sender may reuse the space only once it reads as zero
     __syncthreads();
-    if (tid == 0) {
-      s_next[b & 1] = 0;
-      if (credit) {
-        // updateStatus, pair.cc:624-641: 16-byte status_report to the peer
-        st_release_v2u64(P->peer_credit, cur.credit_val, 0);
-        if (P->peer_mirror) ((volatile PairMirror*)P->peer_mirror)->credit_head = cur.credit_val;
-      }
+    const bool done = ctl.op_done != 0;
+    if (tid == 0 && credit) {
+      // updateStatus, pair.cc:624-641: 16-byte status_report to the peer
+      st_release_v2u64(P->peer_credit, SS.credit_val, 0);
+      if (P->peer_mirror) ((volatile PairMirror*)P->peer_mirror)->credit_head = SS.credit_val;
+      SS.credit_flag = 0;
     }
-    if (last) break;
-    // nobody may still be reading cur (= the buffer the scout fills next iteration) -- guaranteed
-    // by the barrier above; the scout's writes to the other buffer finished before it as well
+    __syncthreads();
+    if (done) break;
   }
-  if (tid == 0) {  // warp 0 lane 0 holds the final cursor
-    P->head = st.head;
-    P->moving_head = st.mh;
-    P->remain = st.remain;
-    P->acc = st.acc;
-    results[blockIdx.x].bytes = st.delivered;
-    results[blockIdx.x].calls = st.ncalls;
+  if (tid == 0) {
+    P->head = SS.head;
+    P->moving_head = SS.mh;
+    P->remain = SS.remain;
+    P->acc = SS.acc;
+    results[blockIdx.x].bytes = SS.delivered;
+    results[blockIdx.x].calls = SS.ncalls;
     uint32_t hm;
     uint64_t rd;
-    rx_probe(ring, cap, st.head, st.remain, hm, rd);
+    rx_probe(ring, cap, SS.head, SS.remain, hm, rd);
     publish_mirror(P->mirror, P, hm, rd);
   }
 }
@@ -751,15 +815,50 @@ k_poll_scan(PairDev* __restrict__ pairs, const int32_t* __restrict__ slots, uint
   }
 }
 
+// =========================================================================
+// k_probe_copy: calibration kernel.  Same decomposition as k_send (one CTA per
+// connection, 4 KiB warp items, same copy primitives) but no framing logic: what
+// this grid shape can reach on this GPU, for src/dst misalignments `mis`.
+// =========================================================================
+__global__ void __launch_bounds__(512, 2)
+k_probe_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t bytes_per_cta, uint64_t stride,
+             uint32_t mis, uint32_t item_bytes, uint32_t dynamic) {
+  __shared__ uint32_t s_next;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint8_t* d = dst + (uint64_t)blockIdx.x * stride;
+  const uint8_t* sp = src + (uint64_t)blockIdx.x * stride + mis;
+  const uint64_t nitems = bytes_per_cta / item_bytes;
+  if (threadIdx.x == 0) s_next = 0;
+  __syncthreads();
+  if (dynamic) {
+    while (true) {
+      uint32_t w = 0;
+      if (lane == 0) w = atomicAdd(&s_next, 1u);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w >= nitems) break;
+      coop_copy<false>(d + (uint64_t)w * item_bytes, sp + (uint64_t)w * item_bytes, item_bytes, lane);
+    }
+  } else {
+    for (uint64_t w = warp; w < nitems; w += nwarps)
+      coop_copy<false>(d + w * item_bytes, sp + w * item_bytes, item_bytes, lane);
+  }
+}
+
+void launch_probe_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,
+                       int threads, uint32_t mis, uint32_t item_bytes, uint32_t dynamic, void* stream) {
+  k_probe_copy<<<nctas, threads, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, bytes_per_cta, stride, mis,
+                                                                         item_bytes, dynamic);
+}
+
 // ---------------------------------------------------------------- launchers
 
 void launch_send(PairDev* pairs, const SendOpDev* ops, OpResult* results, int nops, void* stream) {
   if (nops <= 0) return;
-  k_send<<<nops, kSendThreads, 0, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
+  k_send<<<nops, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
 }
 void launch_recv(PairDev* pairs, const RecvOpDev* ops, OpResult* results, int nops, void* stream) {
   if (nops <= 0) return;
-  k_recv<<<nops, kRecvThreads, 0, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
+  k_recv<<<nops, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
 }
 void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, uint32_t* ready_count,
                       int32_t* ready_slots, int n, void* stream) {

@@ -852,6 +852,19 @@ extern "C" int b200_pairs_recv(const b200_recv_op* ops, size_t nops, int flags, 
   return run_unprepared(1, ops, nops, flags, delivered, stream);
 }
 
+// ================================================================ calibration
+
+extern "C" int b200_probe_copy(void* dst, const void* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,
+                               int threads, uint32_t mis, uint32_t item_bytes, uint32_t dynamic, void* stream) {
+  if (!ensure_init()) return -1;
+  Runtime& r = R();
+  cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
+  launch_probe_copy((uint8_t*)dst, (const uint8_t*)src, bytes_per_cta, stride, nctas, threads, mis, item_bytes,
+                    dynamic, s);
+  r.launches++;
+  return CU_OK(cudaGetLastError()) ? 0 : -1;
+}
+
 // ==================================================================== poller
 
 extern "C" int b200_poller_scan(b200_pair* const* pairs, size_t n, uint32_t* events) {

@@ -221,6 +221,12 @@ int b200_batch_results(b200_batch* b, uint64_t* out, void* stream);
 int b200_batch_calls(b200_batch* b, uint64_t* out);
 void b200_batch_destroy(b200_batch* b);
 
+/* Calibration: copy `bytes_per_cta` bytes per CTA (CTA i works at offset i*stride of src+mis
+ * and dst) with the same one-CTA-per-connection decomposition and copy primitives as the Send
+ * kernel but no framing.  Tells what that grid shape can reach on this GPU. */
+int b200_probe_copy(void* dst, const void* src, uint64_t bytes_per_cta, uint64_t stride, int nctas, int threads,
+                    uint32_t mis, uint32_t item_bytes, uint32_t dynamic, void* stream);
+
 /* Number of kernels this library has launched so far (bench: gpu_launches). */
 uint64_t b200_launch_count(void);
 
