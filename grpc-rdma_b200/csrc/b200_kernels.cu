@@ -580,7 +580,11 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const void* p) {
 }
 
 // Producer: RingBufferPollable::Read (ring_buffer.cc:122-191) + PairPollable::Recv's credit
-// rule (pair.cc:276-284) as integer logic over the frame list.
+// rule (pair.cc:276-284) as integer logic over the frame list.  Two steps per batch of <= 32
+// frames: (1) a minimal sequential walk of the list (header -> footer check -> next header)
+// that leaves frame i in lane i; (2) everything else -- destination capacity, partial reads,
+// pad/footer clearing, the credit threshold, work-item expansion -- lane-parallel with warp
+// scans, exactly like the Send planner.
 __device__ __noinline__ void recv_produce_segment(const RecvOpDev& op, const uint8_t* ring, uint64_t cap,
                                                   ScoutState& SS, WorkItem* q, PipeCtl* ctl, uint32_t lane) {
   const uint64_t mask = cap - 1;
@@ -614,57 +618,131 @@ __device__ __noinline__ void recv_produce_segment(const RecvOpDev& op, const uin
     }
     return __shfl_sync(0xffffffffu, win, (int)(d >> 3));
   };
+  const bool one_call = !(op.flags & kFlagUntilBlocked);
   while (true) {
-    uint64_t r;
-    bool opening = false;
-    if (remain > 0) {
-      r = remain;
-    } else {  // GetReadableSize, ring_buffer.cc:67-97
-      const uint64_t hdr = peek(head);
-      if (hdr == 0 || hdr > cap - kReserved) { last = 1; break; }
-      const uint64_t foot = peek((head + 8 + round_up8(hdr)) & mask);
-      if (foot != kFooter) { last = 1; break; }
-      r = hdr;
-      opening = true;
+    // ---- step 1: walk the list; lane i keeps frame i
+    uint64_t my_r = 0, my_head = 0;
+    bool my_open = false;
+    uint32_t cnt = 0;
+    bool stopped = false;
+    uint64_t h = head;
+    if (remain > 0) {  // rest of a partially consumed frame (its header is already cleared)
+      if (lane == 0) my_r = remain;
+      cnt = 1;
     }
-    const uint64_t n = r < cap_left ? r : cap_left;
-    if (n == 0) { last = 1; break; }
-    if (opening) {  // first touch of this frame, ring_buffer.cc:135-147
-      mh = (head + 8) & mask;
-      head = (head + 16 + round_up8(r)) & mask;
+    const uint32_t want = one_call ? 1u : 32u;
+    while (cnt < want) {  // GetReadableSize, ring_buffer.cc:67-97
+      const uint64_t hdr = peek(h);
+      if (hdr == 0 || hdr > cap - kReserved) { stopped = true; break; }
+      const uint64_t foot = peek((h + 8 + round_up8(hdr)) & mask);
+      if (foot != kFooter) { stopped = true; break; }
+      if (lane == cnt) {
+        my_r = hdr;
+        my_head = h;
+        my_open = true;
+      }
+      h = (h + 16 + round_up8(hdr)) & mask;
+      cnt++;
     }
-    const uint64_t src_off = mh;
-    mh = (mh + n) & mask;
-    remain = r - n;
+    // ---- step 2: Read()/Recv() per frame, all lanes at once
+    const bool valid = lane < cnt;
+    uint64_t r_incl = valid ? my_r : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t t = __shfl_up_sync(0xffffffffu, r_incl, o);
+      if (lane >= (uint32_t)o) r_incl += t;
+    }
+    const uint64_t r_excl = r_incl - (valid ? my_r : 0);
+    const uint64_t room = cap_left > r_excl ? cap_left - r_excl : 0;  // destination space left for this frame
+    const uint64_t n = valid ? (my_r < room ? my_r : room) : 0;     // copy_size = min(readable, capacity)
+    const bool full = valid && n == my_r && n != 0;
+    const unsigned notfull = __ballot_sync(0xffffffffu, !full);
+    const int first_nf = __ffs(notfull) - 1;
+    uint32_t nproc = first_nf < 0 ? 32u : (uint32_t)first_nf;
+    {  // a partially delivered frame is still processed (and is then the last one)
+      const uint64_t n_at = __shfl_sync(0xffffffffu, n, nproc < 32 ? nproc : 0);
+      if (nproc < 32 && n_at != 0) nproc++;
+    }
+    const uint64_t src = my_open ? (my_head + 8) & mask : mh;  // first payload byte to deliver
+    const uint64_t end = (src + n) & mask;
     uint32_t ztail = 0;
-    if (remain == 0) {  // pad + footer, ring_buffer.cc:170-183
-      const uint64_t up = round_up8(mh);
-      ztail = (uint32_t)(up - mh) + 8;
-      mh = ((up & mask) + 8) & mask;
+    uint64_t mh_after = end;
+    if (n == my_r) {  // frame finished: pad + footer, ring_buffer.cc:170-183
+      const uint64_t up = round_up8(end);
+      ztail = (uint32_t)(up - end) + 8;
+      mh_after = ((up & mask) + 8) & mask;
     }
-    const uint32_t zhead = opening ? 8u : 0u;
-    const uint32_t items = (uint32_t)((n + kChunk - 1) / kChunk);
-    for (uint32_t ci = lane; ci < items; ci += 32) {
-      const uint64_t c0 = (uint64_t)ci * kChunk;
-      uint64_t m = n - c0;
-      const bool tail_item = m <= kChunk;
-      if (m > kChunk) m = kChunk;
-      const uint64_t z = (ci == 0 ? zhead : 0u) | ((uint64_t)(tail_item ? ztail : 0u) << 16);
-      publish_item(q, base_item + ci, (src_off + c0) & mask, delivered + c0, z, (uint32_t)m);
+    const uint32_t zhead = my_open ? 8u : 0u;
+    const bool proc = lane < nproc;
+    // credit threshold (pair.cc:276-284): the first frame whose retired bytes push the
+    // accumulator to cap/2 closes the segment
+    uint64_t a_incl = proc ? (uint64_t)zhead + n + ztail : 0;  // internal_bytes_read of this call
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t t = __shfl_up_sync(0xffffffffu, a_incl, o);
+      if (lane >= (uint32_t)o) a_incl += t;
+    }
+    const unsigned cross = __ballot_sync(0xffffffffu, proc && acc + a_incl >= cap / 2);
+    if (cross) {
+      const uint32_t ci = (uint32_t)__ffs(cross) - 1;
+      nproc = ci + 1;
+      credit = 1;
+      credit_val = __shfl_sync(0xffffffffu, mh_after, ci);
+    }
+    if (nproc == 0) {  // nothing deliverable: empty ring, incomplete frame, or no room in dst
+      last = 1;
+      break;
+    }
+    const bool proc2 = lane < nproc;
+    const uint32_t items = proc2 ? (uint32_t)((n + kChunk - 1) / kChunk) : 0;
+    uint32_t items_incl = items;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, items_incl, o);
+      if (lane >= (uint32_t)o) items_incl += t;
+    }
+    const uint32_t nitems = __shfl_sync(0xffffffffu, items_incl, 31);
+    const uint32_t my_first = items_incl - items;
+    // publish in id order: item `it` belongs to the frame f with first[f] <= it < first[f+1]
+    for (uint32_t it0 = 0; it0 < nitems; it0 += 32) {
+      const uint32_t it = it0 + lane;
+      // find the owning frame by asking every lane whether it starts at or before `it`
+      uint32_t f = 0;
+      for (uint32_t g = 0; g < nproc; g++) {
+        const uint32_t fg = __shfl_sync(0xffffffffu, my_first, g);
+        const uint32_t ig = __shfl_sync(0xffffffffu, items, g);
+        if (ig && fg <= it) f = g;
+      }
+      const uint64_t f_src = __shfl_sync(0xffffffffu, src, f);
+      const uint64_t f_n = __shfl_sync(0xffffffffu, n, f);
+      const uint64_t f_dst = delivered + __shfl_sync(0xffffffffu, r_excl, f);
+      const uint32_t f_first = __shfl_sync(0xffffffffu, my_first, f);
+      const uint32_t f_zh = __shfl_sync(0xffffffffu, zhead, f);
+      const uint32_t f_zt = __shfl_sync(0xffffffffu, ztail, f);
+      if (it < nitems) {
+        const uint64_t c0 = (uint64_t)(it - f_first) * kChunk;
+        uint64_t m = f_n - c0;
+        const bool tail_item = m <= kChunk;
+        if (m > kChunk) m = kChunk;
+        const uint64_t z = (c0 == 0 ? f_zh : 0u) | ((uint64_t)(tail_item ? f_zt : 0u) << 16);
+        publish_item(q, base_item + it, (f_src + c0) & mask, f_dst + c0, z, (uint32_t)m);
+      }
     }
     __syncwarp();
-    base_item += items;
-    delivered += n;
-    cap_left -= n;
-    ncalls++;
-    acc += (uint64_t)zhead + n + ztail;  // internal_bytes_read of this call
-    if (acc >= cap / 2) {                // pair.cc:276-284: credit goes out once all of this is cleared
-      credit = 1;
-      credit_val = mh;
-      acc = 0;
-    }
-    if (!(op.flags & kFlagUntilBlocked) || cap_left == 0) { last = 1; break; }
-    if (credit) break;
+    base_item += nitems;
+    // ---- new cursor = state after the last processed frame
+    const uint32_t L = nproc - 1;
+    const bool open_L = __shfl_sync(0xffffffffu, (int)my_open, L) != 0;
+    const uint64_t head_L = __shfl_sync(0xffffffffu, my_head, L);
+    const uint64_t r_L = __shfl_sync(0xffffffffu, my_r, L);
+    const uint64_t n_L = __shfl_sync(0xffffffffu, n, L);
+    const uint64_t moved = __shfl_sync(0xffffffffu, r_excl, L) + n_L;
+    if (open_L) head = (head_L + 16 + round_up8(r_L)) & mask;  // ring_buffer.cc:140-141
+    mh = __shfl_sync(0xffffffffu, mh_after, L);
+    remain = r_L - n_L;
+    acc = credit ? 0 : acc + __shfl_sync(0xffffffffu, a_incl, L);
+    delivered += moved;
+    cap_left -= moved;
+    ncalls += nproc;
+    if (one_call || cap_left == 0 || (stopped && nproc == cnt)) last = 1;
+    if (last || credit) break;
   }
   if (lane == 0) {
     SS.head = head;
@@ -830,17 +908,32 @@ k_probe_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_
   const uint64_t nitems = bytes_per_cta / item_bytes;
   if (threadIdx.x == 0) s_next = 0;
   __syncthreads();
-  if (dynamic) {
+  const bool zero_after = (dynamic & 2) != 0;  // recv-like traffic: read src, write dst, clear src
+  uint8_t* sw = const_cast<uint8_t*>(sp);
+  if (dynamic & 1) {
     while (true) {
       uint32_t w = 0;
       if (lane == 0) w = atomicAdd(&s_next, 1u);
       w = __shfl_sync(0xffffffffu, w, 0);
       if (w >= nitems) break;
-      coop_copy<false>(d + (uint64_t)w * item_bytes, sp + (uint64_t)w * item_bytes, item_bytes, lane);
+      if (zero_after) {
+        coop_copy<true>(d + (uint64_t)w * item_bytes, sp + (uint64_t)w * item_bytes, item_bytes, lane);
+        __syncwarp();
+        coop_zero(sw + (uint64_t)w * item_bytes, item_bytes, lane);
+      } else {
+        coop_copy<false>(d + (uint64_t)w * item_bytes, sp + (uint64_t)w * item_bytes, item_bytes, lane);
+      }
     }
   } else {
-    for (uint64_t w = warp; w < nitems; w += nwarps)
-      coop_copy<false>(d + w * item_bytes, sp + w * item_bytes, item_bytes, lane);
+    for (uint64_t w = warp; w < nitems; w += nwarps) {
+      if (zero_after) {
+        coop_copy<true>(d + w * item_bytes, sp + w * item_bytes, item_bytes, lane);
+        __syncwarp();
+        coop_zero(sw + w * item_bytes, item_bytes, lane);
+      } else {
+        coop_copy<false>(d + w * item_bytes, sp + w * item_bytes, item_bytes, lane);
+      }
+    }
   }
 }
 

@@ -45,9 +45,12 @@ e1.record(stream)
 torch.cuda.synchronize()
 print("torch copy 1 GiB: %.0f GB/s" % (2 * (1 << 30) * 5 / e0.elapsed_time(e1) / 1e6))
 del a, b
-for nctas in (148, 256, 296, 592, 1184):
-    for threads in (256, 512):
-        for mis in (0, 5):
-            for item, dyn in ((4096, 0), (4096, 1), (16384, 0)):
-                print("ctas=%4d thr=%3d mis=%d item=%5d dyn=%d : %6.0f GB/s"
-                      % (nctas, threads, mis, item, dyn, run(nctas, threads, mis, item, dyn)))
+for nctas in (256, 296, 592):
+    for threads in (512,):
+        for mis in (0, 8, 5):
+            for item, dyn in ((4096, 1), (4096, 3), (8192, 3), (16384, 3), (4096, 2)):
+                g = run(nctas, threads, mis, item, dyn)
+                if dyn & 2:
+                    g *= 1.5  # read + write + clear
+                print("ctas=%4d thr=%3d mis=%d item=%5d mode=%d (%s): %6.0f GB/s of traffic"
+                      % (nctas, threads, mis, item, dyn, "copy+clear" if dyn & 2 else "copy", g))
