@@ -109,52 +109,37 @@ __device__ __forceinline__ uint4 shfl_down1_wrap(uint4 a, uint4 next0, uint32_t 
 // is cut out of aligned source vectors i and i+1; vector i+1 is the neighbour lane's load (shuffle),
 // so every source byte is fetched once and kUnroll loads per lane are in flight.  Source vector
 // `nvec` always contains a byte of the range (never faults); vectors beyond it are not touched.
+// One block = up to 32*kUnroll output vectors (4 KiB).  All kUnroll loads of a lane are in
+// flight at once; a short block is handled by predication, never by a slower loop.  Source
+// word w exists iff w <= nvec, output vector v exists iff v < nvec (nvec <= 32*kUnroll).
 template <bool kRingSrc, bool kHi, bool kShift>
-__device__ __noinline__ void copy_vec_shifted(uint8_t* dst, const uint8_t* src_al, uint64_t nvec, unsigned sh,
-                                              uint32_t lane) {
-  const uint4* s = reinterpret_cast<const uint4*>(src_al);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  const uint64_t step = 32ull * kUnroll;
-  const uint64_t nfull = nvec / step * step;
-  if (nfull) {
-    uint4 carry = ld_src16<kRingSrc>(s + lane);
-    for (uint64_t base = 0; base < nfull; base += step) {
-      uint4 A[kUnroll + 1];
-      A[0] = carry;
+__device__ __noinline__ void copy_block_shifted(uint4* __restrict__ d, const uint4* __restrict__ s, uint32_t nvec,
+                                                unsigned sh, uint32_t lane) {
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const uint4* sl = s + lane;
+  uint4* dl = d + lane;
+  uint4 A[kUnroll + 1];
 #pragma unroll
-      for (int k = 1; k < kUnroll; k++) A[k] = ld_src16<kRingSrc>(s + base + 32ull * k + lane);
-      {
-        const uint64_t i = base + step + lane;  // next block's first row; only words <= nvec exist
-        A[kUnroll] = i <= nvec ? ld_src16<kRingSrc>(s + i) : make_uint4(0, 0, 0, 0);
-      }
+  for (int k = 0; k <= kUnroll; k++) A[k] = (32u * k + lane <= nvec) ? ld_src16<kRingSrc>(sl + 32 * k) : zero;
 #pragma unroll
-      for (int k = 0; k < kUnroll; k++) {
-        const uint4 B = shfl_down1_wrap(A[k], A[k + 1], lane);
-        st_stream16(d + base + 32ull * k + lane, shift_window<kHi, kShift>(A[k], B, sh));
-      }
-      carry = A[kUnroll];
-    }
-  }
-  for (uint64_t i = nfull + lane; i < nvec; i += 32) {
-    uint4 A = ld_src16<kRingSrc>(s + i), B = ld_src16<kRingSrc>(s + i + 1);
-    st_stream16(d + i, shift_window<kHi, kShift>(A, B, sh));
+  for (int k = 0; k < kUnroll; k++) {
+    const uint4 B = shfl_down1_wrap(A[k], A[k + 1], lane);
+    if (32u * k + lane < nvec) st_stream16(dl + 32 * k, shift_window<kHi, kShift>(A[k], B, sh));
   }
 }
 
 template <bool kRingSrc>
-__device__ __noinline__ void copy_vec_aligned(uint8_t* dst, const uint8_t* src, uint64_t nvec, uint32_t lane) {
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  const uint64_t step = 32ull * kUnroll;
-  const uint64_t nfull = nvec / step * step;
-  for (uint64_t base = lane; base < nfull; base += step) {
-    uint4 v[kUnroll];
+__device__ __noinline__ void copy_block_aligned(uint4* __restrict__ d, const uint4* __restrict__ s, uint32_t nvec,
+                                                uint32_t lane) {
+  const uint4* sl = s + lane;
+  uint4* dl = d + lane;
+  uint4 v[kUnroll];
 #pragma unroll
-    for (int k = 0; k < kUnroll; k++) v[k] = ld_src16<kRingSrc>(s + base + 32ull * k);
+  for (int k = 0; k < kUnroll; k++)
+    if (32u * k + lane < nvec) v[k] = ld_src16<kRingSrc>(sl + 32 * k);
 #pragma unroll
-    for (int k = 0; k < kUnroll; k++) st_stream16(d + base + 32ull * k, v[k]);
-  }
-  for (uint64_t i = nfull + lane; i < nvec; i += 32) st_stream16(d + i, ld_src16<kRingSrc>(s + i));
+  for (int k = 0; k < kUnroll; k++)
+    if (32u * k + lane < nvec) st_stream16(dl + 32 * k, v[k]);
 }
 
 // Warp-cooperative copy of n bytes, any alignment on either side.  Bulk = aligned 16-byte
@@ -170,19 +155,16 @@ __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint
   n -= head;
   const uint64_t nvec = n >> 4;
   const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15);
-  if (nvec) {
-    if (m == 0) {
-      copy_vec_aligned<kRingSrc>(dst, src, nvec, lane);
-    } else {
-      const uint8_t* sal = src - m;
-      const unsigned sh = (m & 7) * 8;
-      if (m & 8) {
-        if (sh) copy_vec_shifted<kRingSrc, true, true>(dst, sal, nvec, sh, lane);
-        else copy_vec_shifted<kRingSrc, true, false>(dst, sal, nvec, sh, lane);
-      } else {
-        copy_vec_shifted<kRingSrc, false, true>(dst, sal, nvec, sh, lane);
-      }
-    }
+  constexpr uint64_t kBlk = 32ull * kUnroll;
+  const unsigned sh = (m & 7) * 8;
+  const uint4* sal = reinterpret_cast<const uint4*>(src - m);
+  uint4* dv = reinterpret_cast<uint4*>(dst);
+  for (uint64_t v0 = 0; v0 < nvec; v0 += kBlk) {
+    const uint32_t nb = (uint32_t)(nvec - v0 < kBlk ? nvec - v0 : kBlk);
+    if (m == 0) copy_block_aligned<kRingSrc>(dv + v0, sal + v0, nb, lane);
+    else if (!(m & 8)) copy_block_shifted<kRingSrc, false, true>(dv + v0, sal + v0, nb, sh, lane);
+    else if (sh) copy_block_shifted<kRingSrc, true, true>(dv + v0, sal + v0, nb, sh, lane);
+    else copy_block_shifted<kRingSrc, true, false>(dv + v0, sal + v0, nb, sh, lane);
   }
   const uint64_t done = nvec << 4;
   const uint64_t tail = n - done;
