@@ -145,20 +145,28 @@ __device__ __noinline__ void copy_block_aligned(uint4* __restrict__ d, const uin
 // Warp-cooperative copy of n bytes, any alignment on either side.  Bulk = aligned 16-byte
 // stores; the <16-byte head and tail use one byte per lane.
 template <bool kRingSrc>
+__device__ __forceinline__ uint8_t ld_byte(const uint8_t* p) {
+  return kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(p) : __ldg(p);
+}
+
+template <bool kRingSrc>
 __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint64_t n, uint32_t lane) {
   if (n == 0) return;
   uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
   if (head > n) head = n;
-  if (lane < head) dst[lane] = kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(src + lane) : src[lane];
-  dst += head;
-  src += head;
-  n -= head;
-  const uint64_t nvec = n >> 4;
-  const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15);
+  const uint64_t nvec = (n - head) >> 4;
+  const uint64_t tail = n - head - (nvec << 4);
+  // edge bytes: loads go out first so they are in flight together with the vector loads,
+  // the dependent byte stores come last
+  uint8_t hb = 0, tb = 0;
+  if (lane < head) hb = ld_byte<kRingSrc>(src + lane);
+  if (lane < tail) tb = ld_byte<kRingSrc>(src + head + (nvec << 4) + lane);
+  const uint8_t* vsrc = src + head;
+  const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(vsrc) & 15);
   constexpr uint64_t kBlk = 32ull * kUnroll;
   const unsigned sh = (m & 7) * 8;
-  const uint4* sal = reinterpret_cast<const uint4*>(src - m);
-  uint4* dv = reinterpret_cast<uint4*>(dst);
+  const uint4* sal = reinterpret_cast<const uint4*>(vsrc - m);
+  uint4* dv = reinterpret_cast<uint4*>(dst + head);
   for (uint64_t v0 = 0; v0 < nvec; v0 += kBlk) {
     const uint32_t nb = (uint32_t)(nvec - v0 < kBlk ? nvec - v0 : kBlk);
     if (m == 0) copy_block_aligned<kRingSrc>(dv + v0, sal + v0, nb, lane);
@@ -166,10 +174,8 @@ __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint
     else if (sh) copy_block_shifted<kRingSrc, true, true>(dv + v0, sal + v0, nb, sh, lane);
     else copy_block_shifted<kRingSrc, true, false>(dv + v0, sal + v0, nb, sh, lane);
   }
-  const uint64_t done = nvec << 4;
-  const uint64_t tail = n - done;
-  if (lane < tail)
-    dst[done + lane] = kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(src + done + lane) : src[done + lane];
+  if (lane < head) dst[lane] = hb;
+  if (lane < tail) dst[head + (nvec << 4) + lane] = tb;
 }
 
 // Warp-cooperative zero fill of n bytes at p (any alignment).
@@ -491,14 +497,35 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
     // ---------------------------------------------- move bytes
     uint64_t a, b, c;
     uint32_t n;
+    // A tiny item (<= 32 bytes: an HTTP/2 frame header) costs a full trip to memory for a few
+    // bytes.  Its one-byte-per-lane load is issued, then the warp goes on with the next item and
+    // completes the tiny one afterwards, so the two trips overlap.
+    bool pend = false;
+    uint64_t pb = 0;
+    uint32_t pn = 0;
+    uint8_t pbyte = 0;
+    auto finish_tiny = [&]() {
+      if (lane < pn) ring[(pb + lane) & mask] = pbyte;
+      pend = false;
+    };
     while (claim_item(q, &ctl, lane, a, b, c, n)) {
       const uint8_t* src = reinterpret_cast<const uint8_t*>(a);
       if (c != 0 && lane == 0) *reinterpret_cast<uint64_t*>(ring + ((b + cap - 8) & mask)) = c;  // AppendHeader
+      if (n <= 32) {
+        if (pend) finish_tiny();
+        pb = b;
+        pn = n;
+        pbyte = lane < n ? __ldg(src + lane) : 0;
+        pend = true;
+        continue;
+      }
       uint64_t seg1 = cap - b;
       if (seg1 > n) seg1 = n;
       coop_copy<false>(ring + b, src, seg1, lane);
       if (n > seg1) coop_copy<false>(ring, src + seg1, n - seg1, lane);  // wrap: WR1 at remote+0
+      if (pend) finish_tiny();
     }
+    if (pend) finish_tiny();
     // footers last: a frame is complete for the reader only when header != 0 and footer == ~0
     // (ring_buffer.cc:75-96), so everything else of the segment is made visible first
     if (sys_scope) __threadfence_system();
@@ -788,7 +815,37 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
     if (warp == 0) recv_produce_segment(op, ring, cap, SS, q, &ctl, lane);
     uint64_t a, b, c;
     uint32_t n;
+    auto clear_item = [&](uint64_t ia, uint64_t ic, uint32_t in) {  // clear-on-read: exactly what the item retired
+      const uint32_t zhead = (uint32_t)(ic & 0xffff), ztail = (uint32_t)(ic >> 16);
+      const uint64_t zs = (ia + cap - zhead) & mask;
+      const uint64_t zl = (uint64_t)zhead + in + ztail;
+      uint64_t z1 = cap - zs;
+      if (z1 > zl) z1 = zl;
+      coop_zero(ring + zs, z1, lane);
+      if (zl > z1) coop_zero(ring, zl - z1, lane);
+    };
+    // tiny items (<= 32 bytes) overlap with the next item, see k_send
+    bool pend = false;
+    uint64_t pa = 0, pb = 0, pc = 0;
+    uint32_t pn = 0;
+    uint8_t pbyte = 0;
+    auto finish_tiny = [&]() {
+      if (lane < pn) op.dst[pb + lane] = pbyte;
+      __syncwarp();
+      clear_item(pa, pc, pn);
+      pend = false;
+    };
     while (claim_item(q, &ctl, lane, a, b, c, n)) {
+      if (n <= 32) {
+        if (pend) finish_tiny();
+        pa = a;
+        pb = b;
+        pc = c;
+        pn = n;
+        pbyte = lane < n ? *reinterpret_cast<const volatile uint8_t*>(ring + ((a + lane) & mask)) : 0;
+        pend = true;
+        continue;
+      }
       // ---- scatter
       uint8_t* dst = op.dst + b;
       uint64_t seg1 = cap - a;
@@ -796,15 +853,10 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
       coop_copy<true>(dst, ring + a, seg1, lane);
       if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, lane);
       __syncwarp();  // every lane's loads are done before any lane clears
-      // ---- clear-on-read: exactly what this item retired
-      const uint32_t zhead = (uint32_t)(c & 0xffff), ztail = (uint32_t)(c >> 16);
-      const uint64_t zs = (a + cap - zhead) & mask;
-      const uint64_t zl = (uint64_t)zhead + n + ztail;
-      uint64_t z1 = cap - zs;
-      if (z1 > zl) z1 = zl;
-      coop_zero(ring + zs, z1, lane);
-      if (zl > z1) coop_zero(ring, zl - z1, lane);
+      clear_item(a, c, n);
+      if (pend) finish_tiny();
     }
+    if (pend) finish_tiny();
     const bool credit = ld_shared_volatile(&SS.credit_flag) != 0;  // stable: the producer finished this segment
     if (credit) __threadfence_system();       // the sender may reuse the space only once it reads as zero
     __syncthreads();
