@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--msg-bytes", type=int, default=MSG_BYTES)
     ap.add_argument("--ring-kb", type=int, default=RING_KB)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
-    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "zerocopy", "staged"])
+    ap.add_argument("--e2e-mode", default="staged", choices=["auto", "zerocopy", "staged"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -223,7 +223,7 @@ def main():
     del i, row, offs
     dst = torch.zeros(conns * total, dtype=torch.uint8, device=dev)
 
-    def build_batches(src_ptr, dst_ptr):
+    def build_batches(src_ptr, dst_ptr, extra_flags=0):
         sops, rops, keep = [], [], []
         for c in range(conns):
             off, sl = 0, []
@@ -234,7 +234,8 @@ def main():
             keep.append(arr)
             sops.append((pairs[c][0], arr, len(lens), 0))
             rops.append((pairs[c][1], dst_ptr + c * total, total))
-        return pkg.Batch("send", sops, pkg.UNTIL_BLOCKED), pkg.Batch("recv", rops, pkg.UNTIL_BLOCKED), keep
+        fl = pkg.UNTIL_BLOCKED | extra_flags
+        return pkg.Batch("send", sops, fl), pkg.Batch("recv", rops, fl), keep
 
     bs, br, keep = build_batches(src.data_ptr(), dst.data_ptr())
     # an explicit stream: the library treats a NULL stream handle as "its own stream", and
@@ -369,24 +370,21 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
     for mode in modes:
         if mode == "zerocopy":
             # kernels address the pinned host slices / destinations directly: bytes cross PCIe once each way
-            bs, br, keep = build_batches(hsrc, hdst)
-            stage = None
+            bs, br, keep = build_batches(hsrc, hdst, pkg.ZEROCOPY)
 
             def step():
                 bs.launch(sh)
                 br.launch(sh)
         else:
-            dsrc = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            ddst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            bs, br, keep = build_batches(dsrc.data_ptr(), ddst.data_ptr())
+            # the library's host-staged path: per lane H2D -> k_send ... k_recv -> D2H on internal streams
+            bs, br, keep = build_batches(hsrc, hdst)
 
             def step():
-                L.b200_memcpy(dsrc.data_ptr(), hsrc, nbytes, 0, sh)
-                bs.launch(sh)
-                br.launch(sh)
-                L.b200_memcpy(hdst, ddst.data_ptr(), nbytes, 1, sh)
+                bs.launch(None)
+                br.launch(None)
         hd[:] = 0
         step()
+        L.b200_lanes_join(None)
         torch.cuda.synchronize()
         ok = bool(np.array_equal(hs, hd))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -394,8 +392,10 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
             dist.barrier()
         torch.cuda.synchronize()
         e0.record(stream)
+        L.b200_lanes_fork(sh)        # lanes start after e0 ...
         for _ in range(K):
             step()
+        L.b200_lanes_join(sh)        # ... and e1 waits for every lane
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)

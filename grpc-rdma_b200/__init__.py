@@ -17,11 +17,11 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libb200rdma.so")
+LIB_PATH = os.environ.get("B200RDMA_LIB") or os.path.join(PKG_DIR, "lib", "libb200rdma.so")  # env: experiment builds
 HEADER = os.path.join(ROOT, "include", "b200_pair.h")
 
 ADDRESS_BYTES = 48
-ONE_CALL, UNTIL_BLOCKED, ASYNC = 0, 1, 2
+ONE_CALL, UNTIL_BLOCKED, ASYNC, ZEROCOPY = 0, 1, 2, 4
 EV_READABLE, EV_WRITABLE = 0x1, 0x4
 STATUS = ["UNINITIALIZED", "INITIALIZED", "CONNECTED", "HALF_CLOSED", "DISCONNECTED", "ERROR"]
 
@@ -101,6 +101,8 @@ _SIGS = {
     "b200_batch_prepare_recv": (C.c_void_p, [C.POINTER(RecvOp), C.c_size_t, C.c_int]),
     "b200_batch_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_batch_results": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "b200_lanes_fork": (C.c_int, [C.c_void_p]),
+    "b200_lanes_join": (C.c_int, [C.c_void_p]),
     "b200_batch_calls": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "b200_batch_destroy": (None, [C.c_void_p]),
     "b200_probe_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint32,

@@ -156,11 +156,9 @@ __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint
   if (head > n) head = n;
   const uint64_t nvec = (n - head) >> 4;
   const uint64_t tail = n - head - (nvec << 4);
-  // edge bytes: loads go out first so they are in flight together with the vector loads,
-  // the dependent byte stores come last
-  uint8_t hb = 0, tb = 0;
-  if (lane < head) hb = ld_byte<kRingSrc>(src + lane);
-  if (lane < tail) tb = ld_byte<kRingSrc>(src + head + (nvec << 4) + lane);
+  // <16-byte edges: one byte per lane
+  if (lane < head) dst[lane] = ld_byte<kRingSrc>(src + lane);
+  if (lane < tail) dst[head + (nvec << 4) + lane] = ld_byte<kRingSrc>(src + head + (nvec << 4) + lane);
   const uint8_t* vsrc = src + head;
   const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(vsrc) & 15);
   constexpr uint64_t kBlk = 32ull * kUnroll;
@@ -174,8 +172,6 @@ __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint
     else if (sh) copy_block_shifted<kRingSrc, true, true>(dv + v0, sal + v0, nb, sh, lane);
     else copy_block_shifted<kRingSrc, true, false>(dv + v0, sal + v0, nb, sh, lane);
   }
-  if (lane < head) dst[lane] = hb;
-  if (lane < tail) dst[head + (nvec << 4) + lane] = tb;
 }
 
 // Warp-cooperative zero fill of n bytes at p (any alignment).
@@ -497,35 +493,14 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
     // ---------------------------------------------- move bytes
     uint64_t a, b, c;
     uint32_t n;
-    // A tiny item (<= 32 bytes: an HTTP/2 frame header) costs a full trip to memory for a few
-    // bytes.  Its one-byte-per-lane load is issued, then the warp goes on with the next item and
-    // completes the tiny one afterwards, so the two trips overlap.
-    bool pend = false;
-    uint64_t pb = 0;
-    uint32_t pn = 0;
-    uint8_t pbyte = 0;
-    auto finish_tiny = [&]() {
-      if (lane < pn) ring[(pb + lane) & mask] = pbyte;
-      pend = false;
-    };
     while (claim_item(q, &ctl, lane, a, b, c, n)) {
       const uint8_t* src = reinterpret_cast<const uint8_t*>(a);
       if (c != 0 && lane == 0) *reinterpret_cast<uint64_t*>(ring + ((b + cap - 8) & mask)) = c;  // AppendHeader
-      if (n <= 32) {
-        if (pend) finish_tiny();
-        pb = b;
-        pn = n;
-        pbyte = lane < n ? __ldg(src + lane) : 0;
-        pend = true;
-        continue;
-      }
       uint64_t seg1 = cap - b;
       if (seg1 > n) seg1 = n;
       coop_copy<false>(ring + b, src, seg1, lane);
       if (n > seg1) coop_copy<false>(ring, src + seg1, n - seg1, lane);  // wrap: WR1 at remote+0
-      if (pend) finish_tiny();
     }
-    if (pend) finish_tiny();
     // footers last: a frame is complete for the reader only when header != 0 and footer == ~0
     // (ring_buffer.cc:75-96), so everything else of the segment is made visible first
     if (sys_scope) __threadfence_system();
@@ -824,28 +799,7 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
       coop_zero(ring + zs, z1, lane);
       if (zl > z1) coop_zero(ring, zl - z1, lane);
     };
-    // tiny items (<= 32 bytes) overlap with the next item, see k_send
-    bool pend = false;
-    uint64_t pa = 0, pb = 0, pc = 0;
-    uint32_t pn = 0;
-    uint8_t pbyte = 0;
-    auto finish_tiny = [&]() {
-      if (lane < pn) op.dst[pb + lane] = pbyte;
-      __syncwarp();
-      clear_item(pa, pc, pn);
-      pend = false;
-    };
     while (claim_item(q, &ctl, lane, a, b, c, n)) {
-      if (n <= 32) {
-        if (pend) finish_tiny();
-        pa = a;
-        pb = b;
-        pc = c;
-        pn = n;
-        pbyte = lane < n ? *reinterpret_cast<const volatile uint8_t*>(ring + ((a + lane) & mask)) : 0;
-        pend = true;
-        continue;
-      }
       // ---- scatter
       uint8_t* dst = op.dst + b;
       uint64_t seg1 = cap - a;
@@ -854,9 +808,7 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
       if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, lane);
       __syncwarp();  // every lane's loads are done before any lane clears
       clear_item(a, c, n);
-      if (pend) finish_tiny();
     }
-    if (pend) finish_tiny();
     const bool credit = ld_shared_volatile(&SS.credit_flag) != 0;  // stable: the producer finished this segment
     if (credit) __threadfence_system();       // the sender may reuse the space only once it reads as zero
     __syncthreads();

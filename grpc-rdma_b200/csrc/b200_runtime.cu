@@ -88,6 +88,19 @@ struct b200_pair {
   bool in_poller = false;
 };
 
+constexpr int kLanes = 8;  // internal streams of the host-staged path
+
+struct CopyRun {  // one cudaMemcpyAsync
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+
+struct LanePlan {  // the ops of a lane are contiguous in d_ops
+  int first_op = 0, nops = 0;
+  std::vector<CopyRun> copies;
+};
+
 struct b200_batch {
   int kind = 0;  // 0 send, 1 recv
   int nops = 0;
@@ -96,6 +109,12 @@ struct b200_batch {
   SliceDev* d_slices = nullptr;
   OpResult* d_results = nullptr;
   OpResult* h_results = nullptr;  // pinned
+  // host-staged path: slices / destinations are pinned HOST memory; the batch owns a device
+  // staging arena and runs as kLanes independent H2D -> kernel (-> D2H) pipelines
+  bool staged = false;
+  uint8_t* d_stage = nullptr;
+  std::vector<int> perm;  // perm[k] = caller's index of device op k
+  LanePlan lanes[kLanes];
 };
 
 namespace {
@@ -109,6 +128,9 @@ struct Runtime {
   Config cfg;
   cudaStream_t stream = nullptr;       // single-call + setup stream
   cudaStream_t poll_stream = nullptr;  // readiness scans
+  cudaStream_t lane_streams[kLanes] = {};
+  cudaEvent_t lane_events[kLanes] = {};
+  cudaEvent_t fork_event = nullptr;
   PairDev* d_pairs = nullptr;
   PairMirror* h_mirrors = nullptr;  // pinned, mapped
   std::vector<b200_pair*> all_pairs;
@@ -217,6 +239,11 @@ extern "C" int b200_init(int device) {
 
   if (!CU_OK(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking))) return -1;
   if (!CU_OK(cudaStreamCreateWithFlags(&r.poll_stream, cudaStreamNonBlocking))) return -1;
+  for (int i = 0; i < kLanes; i++) {
+    if (!CU_OK(cudaStreamCreateWithFlags(&r.lane_streams[i], cudaStreamNonBlocking))) return -1;
+    if (!CU_OK(cudaEventCreateWithFlags(&r.lane_events[i], cudaEventDisableTiming))) return -1;
+  }
+  if (!CU_OK(cudaEventCreateWithFlags(&r.fork_event, cudaEventDisableTiming))) return -1;
   if (!CU_OK(cudaMalloc(&r.d_pairs, sizeof(PairDev) * kMaxPairs))) return -1;
   if (!CU_OK(cudaMemset(r.d_pairs, 0, sizeof(PairDev) * kMaxPairs))) return -1;
   if (!CU_OK(cudaHostAlloc(&r.h_mirrors, sizeof(PairMirror) * kMaxPairs, cudaHostAllocMapped | cudaHostAllocPortable)))
@@ -277,6 +304,11 @@ extern "C" void b200_shutdown(void) {
   r.bounce_tx_cap = r.bounce_rx_cap = 0;
   cudaStreamDestroy(r.stream);
   cudaStreamDestroy(r.poll_stream);
+  for (int i = 0; i < kLanes; i++) {
+    cudaStreamDestroy(r.lane_streams[i]);
+    cudaEventDestroy(r.lane_events[i]);
+  }
+  cudaEventDestroy(r.fork_event);
   r.inited = false;
 }
 
@@ -725,6 +757,31 @@ extern "C" uint64_t b200_pair_recv(b200_pair* p, void* dst, uint64_t cap) {
 
 // ===================================================================== batch
 
+// 0 = unregistered host, 1 = registered/pinned host, 2 = device or managed
+static int mem_class(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (a.type == cudaMemoryTypeHost) return 1;
+  if (a.type == cudaMemoryTypeUnregistered) return 0;
+  return 2;
+}
+
+static int lane_of(const b200_pair* p) {
+  int key = p->slot;
+  if (p->peer_local && p->peer_local->slot < key) key = p->peer_local->slot;
+  return (key >> 1) % kLanes;  // both ends of a loopback connection share a lane: per-connection order
+}
+
+static size_t stage_place(size_t& cursor, const void* host_ptr, size_t bytes) {
+  // keep the host buffer's alignment modulo 256 so the kernels see the same (mis)alignment
+  size_t off = ((cursor + 255) & ~(size_t)255) + ((uintptr_t)host_ptr & 255);
+  cursor = off + bytes;
+  return off;
+}
+
 static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int flags) {
   if (!ensure_init()) return nullptr;
   Runtime& r = R();
@@ -733,51 +790,125 @@ static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int 
   b->kind = kind;
   b->nops = (int)nops;
   b->flags = flags;
+  const b200_send_op* sops = (const b200_send_op*)ops_v;
+  const b200_recv_op* rops = (const b200_recv_op*)ops_v;
   bool ok = true;
-  if (kind == 0) {
-    const b200_send_op* ops = (const b200_send_op*)ops_v;
+  // ---- where do the payload bytes live?
+  int cls = -1;
+  for (size_t i = 0; ok && i < nops; i++) {
+    const b200_pair* pr = kind == 0 ? sops[i].pair : rops[i].pair;
+    if (!pr) {
+      set_err("batch: null pair");
+      ok = false;
+      break;
+    }
+    const void* probe = nullptr;
+    if (kind == 0) {
+      for (size_t j = 0; j < sops[i].nslices && !probe; j++)
+        if (sops[i].slices[j].len) probe = sops[i].slices[j].ptr;
+    } else if (rops[i].cap) {
+      probe = rops[i].dst;
+    }
+    if (!probe) continue;
+    const int c = mem_class(probe);
+    if (c == 0) {
+      set_err("batch: slices / destinations must be GPU-addressable (device memory, b200_mem_alloc_host or "
+              "b200_mem_register_host); unregistered host memory is only accepted by b200_pair_send/recv");
+      ok = false;
+    } else if (cls >= 0 && c != cls) {
+      set_err("batch: host and device buffers cannot be mixed in one batch");
+      ok = false;
+    }
+    cls = c;
+  }
+  b->staged = ok && cls == 1 && !(flags & B200_BATCH_ZEROCOPY);
+  // ---- device order of the ops: lane-sorted for the staged path, caller's order otherwise
+  b->perm.resize(nops);
+  if (ok && b->staged) {
+    int k = 0;
+    for (int L = 0; L < kLanes; L++) {
+      b->lanes[L].first_op = k;
+      for (size_t i = 0; i < nops; i++)
+        if (lane_of(kind == 0 ? sops[i].pair : rops[i].pair) == L) b->perm[k++] = (int)i;
+      b->lanes[L].nops = k - b->lanes[L].first_op;
+    }
+  } else {
+    for (size_t i = 0; i < nops; i++) b->perm[i] = (int)i;
+  }
+  const uint32_t kflags = (uint32_t)(flags & B200_BATCH_UNTIL_BLOCKED);
+  if (ok && kind == 0) {
     size_t total_slices = 0;
-    for (size_t i = 0; i < nops; i++) total_slices += ops[i].nslices;
-    std::vector<SendOpDev> h(nops);
+    for (size_t i = 0; i < nops; i++) total_slices += sops[i].nslices;
+    std::vector<SendOpDev> h(nops ? nops : 1);
     std::vector<SliceDev> hs(total_slices ? total_slices : 1);
+    std::vector<size_t> stage_off(total_slices ? total_slices : 1, 0);
     ok = CU_OK(cudaMalloc(&b->d_slices, sizeof(SliceDev) * hs.size())) &&
          CU_OK(cudaMalloc(&b->d_ops, sizeof(SendOpDev) * (nops ? nops : 1)));
-    size_t off = 0;
-    for (size_t i = 0; ok && i < nops; i++) {
-      if (!ops[i].pair) {
-        set_err("batch: null pair");
-        ok = false;
-        break;
+    size_t off = 0, cursor = 0;
+    struct Run { int lane; const uint8_t* src; size_t bytes, stage; };
+    std::vector<Run> runs;
+    for (size_t k = 0; ok && k < nops; k++) {
+      const b200_send_op& o = sops[b->perm[k]];
+      h[k].slot = o.pair->slot;
+      h[k].flags = kflags;
+      h[k].slices = b->d_slices + off;
+      h[k].nslices = o.nslices;
+      h[k].byte_idx = o.byte_idx;
+      const int L = b->staged ? lane_of(o.pair) : 0;
+      const uint8_t* run_end = nullptr;
+      for (size_t j = 0; j < o.nslices; j++) {
+        const uint8_t* ptr = (const uint8_t*)o.slices[j].ptr;
+        const uint64_t len = o.slices[j].len;
+        hs[off + j].ptr = ptr;
+        hs[off + j].len = len;
+        if (b->staged && len) {
+          // adjacent slices (a message cut into DATA frames) are staged by one copy
+          if (runs.empty() || runs.back().lane != L || ptr != run_end) {
+            Run nr = {L, ptr, 0, 0};
+            nr.stage = stage_place(cursor, ptr, 0);
+            runs.push_back(nr);
+          }
+          stage_off[off + j] = runs.back().stage + runs.back().bytes;
+          runs.back().bytes += len;
+          cursor = runs.back().stage + runs.back().bytes;
+          run_end = ptr + len;
+        }
       }
-      h[i].slot = ops[i].pair->slot;
-      h[i].flags = (uint32_t)(flags & B200_BATCH_UNTIL_BLOCKED);
-      h[i].slices = b->d_slices + off;
-      h[i].nslices = ops[i].nslices;
-      h[i].byte_idx = ops[i].byte_idx;
-      for (size_t j = 0; j < ops[i].nslices; j++) {
-        hs[off + j].ptr = (const uint8_t*)ops[i].slices[j].ptr;
-        hs[off + j].len = ops[i].slices[j].len;
-      }
-      off += ops[i].nslices;
+      off += o.nslices;
+    }
+    if (ok && b->staged) {
+      ok = CU_OK(cudaMalloc(&b->d_stage, cursor + 256));
+      for (size_t q = 0; ok && q < total_slices; q++)
+        if (hs[q].len) hs[q].ptr = b->d_stage + stage_off[q];
+      for (const Run& rn : runs) b->lanes[rn.lane].copies.push_back({b->d_stage + rn.stage, rn.src, rn.bytes});
     }
     ok = ok && CU_OK(cudaMemcpy(b->d_slices, hs.data(), sizeof(SliceDev) * hs.size(), cudaMemcpyHostToDevice)) &&
-         CU_OK(cudaMemcpy(b->d_ops, h.data(), sizeof(SendOpDev) * nops, cudaMemcpyHostToDevice));
-  } else {
-    const b200_recv_op* ops = (const b200_recv_op*)ops_v;
-    std::vector<RecvOpDev> h(nops);
+         CU_OK(cudaMemcpy(b->d_ops, h.data(), sizeof(SendOpDev) * (nops ? nops : 1), cudaMemcpyHostToDevice));
+  } else if (ok) {
+    std::vector<RecvOpDev> h(nops ? nops : 1);
     ok = CU_OK(cudaMalloc(&b->d_ops, sizeof(RecvOpDev) * (nops ? nops : 1)));
-    for (size_t i = 0; ok && i < nops; i++) {
-      if (!ops[i].pair) {
-        set_err("batch: null pair");
-        ok = false;
-        break;
-      }
-      h[i].slot = ops[i].pair->slot;
-      h[i].flags = (uint32_t)(flags & B200_BATCH_UNTIL_BLOCKED);
-      h[i].dst = (uint8_t*)ops[i].dst;
-      h[i].cap = ops[i].cap;
+    size_t cursor = 0;
+    std::vector<size_t> place(nops ? nops : 1, 0);
+    for (size_t k = 0; k < nops; k++) {
+      const b200_recv_op& o = rops[b->perm[k]];
+      h[k].slot = o.pair->slot;
+      h[k].flags = kflags;
+      h[k].dst = (uint8_t*)o.dst;
+      h[k].cap = o.cap;
+      if (b->staged && o.cap) place[k] = stage_place(cursor, o.dst, o.cap);
     }
-    ok = ok && CU_OK(cudaMemcpy(b->d_ops, h.data(), sizeof(RecvOpDev) * nops, cudaMemcpyHostToDevice));
+    if (ok && b->staged) {
+      ok = CU_OK(cudaMalloc(&b->d_stage, cursor + 256));
+      for (size_t k = 0; ok && k < nops; k++) {
+        const b200_recv_op& o = rops[b->perm[k]];
+        if (!o.cap) continue;
+        h[k].dst = b->d_stage + place[k];
+        // the whole destination window comes back: callers size it to what they expect, like
+        // the endpoint's max(256, GetReadableSize()) slice (rdma_bp_posix.cc:308-317)
+        b->lanes[lane_of(o.pair)].copies.push_back({o.dst, b->d_stage + place[k], (size_t)o.cap});
+      }
+    }
+    ok = ok && CU_OK(cudaMemcpy(b->d_ops, h.data(), sizeof(RecvOpDev) * (nops ? nops : 1), cudaMemcpyHostToDevice));
   }
   ok = ok && CU_OK(cudaMalloc(&b->d_results, sizeof(OpResult) * (nops ? nops : 1))) &&
        CU_OK(cudaHostAlloc(&b->h_results, sizeof(OpResult) * (nops ? nops : 1), cudaHostAllocPortable));
@@ -795,33 +926,84 @@ extern "C" b200_batch* b200_batch_prepare_recv(const b200_recv_op* ops, size_t n
   return prepare_common(1, ops, nops, flags);
 }
 
+extern "C" int b200_lanes_fork(void* stream) {
+  if (!ensure_init() || !stream) return -1;
+  Runtime& r = R();
+  if (!CU_OK(cudaEventRecord(r.fork_event, (cudaStream_t)stream))) return -1;
+  for (int L = 0; L < kLanes; L++)
+    if (!CU_OK(cudaStreamWaitEvent(r.lane_streams[L], r.fork_event, 0))) return -1;
+  return 0;
+}
+
+extern "C" int b200_lanes_join(void* stream) {
+  if (!ensure_init()) return -1;
+  Runtime& r = R();
+  for (int L = 0; L < kLanes; L++) {
+    if (stream) {
+      if (!CU_OK(cudaEventRecord(r.lane_events[L], r.lane_streams[L])) ||
+          !CU_OK(cudaStreamWaitEvent((cudaStream_t)stream, r.lane_events[L], 0)))
+        return -1;
+    } else if (!CU_OK(cudaStreamSynchronize(r.lane_streams[L]))) {
+      return -1;
+    }
+  }
+  return 0;
+}
+
 extern "C" int b200_batch_launch(b200_batch* b, void* stream) {
   if (!b) return -1;
   Runtime& r = R();
-  cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
   if (b->nops == 0) return 0;
-  if (b->kind == 0) launch_send(r.d_pairs, (const SendOpDev*)b->d_ops, b->d_results, b->nops, s);
-  else launch_recv(r.d_pairs, (const RecvOpDev*)b->d_ops, b->d_results, b->nops, s);
-  r.launches++;
-  return CU_OK(cudaGetLastError()) ? 0 : -1;
+  if (!b->staged) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
+    if (b->kind == 0) launch_send(r.d_pairs, (const SendOpDev*)b->d_ops, b->d_results, b->nops, s);
+    else launch_recv(r.d_pairs, (const RecvOpDev*)b->d_ops, b->d_results, b->nops, s);
+    r.launches++;
+    return CU_OK(cudaGetLastError()) ? 0 : -1;
+  }
+  // host-staged: every lane is its own stream; a connection always maps to the same lane, so
+  // Send and Recv of one connection stay ordered while lanes overlap H2D, kernels and D2H
+  if (stream && b200_lanes_fork(stream) != 0) return -1;
+  for (int L = 0; L < kLanes; L++) {
+    LanePlan& lp = b->lanes[L];
+    if (lp.nops == 0) continue;
+    cudaStream_t s = r.lane_streams[L];
+    if (b->kind == 0) {
+      for (const CopyRun& c : lp.copies)
+        if (!CU_OK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyHostToDevice, s))) return -1;
+      launch_send(r.d_pairs, (const SendOpDev*)b->d_ops + lp.first_op, b->d_results + lp.first_op, lp.nops, s);
+    } else {
+      launch_recv(r.d_pairs, (const RecvOpDev*)b->d_ops + lp.first_op, b->d_results + lp.first_op, lp.nops, s);
+      for (const CopyRun& c : lp.copies)
+        if (!CU_OK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s))) return -1;
+    }
+    r.launches++;
+    if (!CU_OK(cudaGetLastError())) return -1;
+  }
+  if (stream && b200_lanes_join(stream) != 0) return -1;
+  return 0;
 }
 
 extern "C" int b200_batch_results(b200_batch* b, uint64_t* out, void* stream) {
   if (!b) return -1;
   Runtime& r = R();
-  cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
   if (b->nops == 0) return 0;
+  cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
+  if (b->staged) {
+    for (int L = 0; L < kLanes; L++)
+      if (b->lanes[L].nops && !CU_OK(cudaStreamSynchronize(r.lane_streams[L]))) return -1;
+  }
   if (!CU_OK(cudaMemcpyAsync(b->h_results, b->d_results, sizeof(OpResult) * b->nops, cudaMemcpyDeviceToHost, s)) ||
       !CU_OK(cudaStreamSynchronize(s)))
     return -1;
   if (out)
-    for (int i = 0; i < b->nops; i++) out[i] = b->h_results[i].bytes;
+    for (int k = 0; k < b->nops; k++) out[b->perm[k]] = b->h_results[k].bytes;
   return 0;
 }
 
 extern "C" int b200_batch_calls(b200_batch* b, uint64_t* out) {
   if (!b || !out) return -1;
-  for (int i = 0; i < b->nops; i++) out[i] = b->h_results[i].calls;
+  for (int k = 0; k < b->nops; k++) out[b->perm[k]] = b->h_results[k].calls;
   return 0;
 }
 
@@ -830,6 +1012,7 @@ extern "C" void b200_batch_destroy(b200_batch* b) {
   if (b->d_ops) cudaFree(b->d_ops);
   if (b->d_slices) cudaFree(b->d_slices);
   if (b->d_results) cudaFree(b->d_results);
+  if (b->d_stage) cudaFree(b->d_stage);
   if (b->h_results) cudaFreeHost(b->h_results);
   delete b;
 }

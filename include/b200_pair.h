@@ -189,6 +189,19 @@ int b200_poller_scan(b200_pair* const* pairs, size_t n, uint32_t* events);
 #define B200_BATCH_ONE_CALL 0x0
 #define B200_BATCH_UNTIL_BLOCKED 0x1
 #define B200_BATCH_ASYNC 0x2 /* do not synchronise; results valid after stream sync */
+#define B200_BATCH_ZEROCOPY 0x4 /* pinned HOST buffers are dereferenced by the kernels over PCIe */
+/*
+ * Where the bytes live decides the path of a batch:
+ *   device memory        kernels work in place (one launch per batch);
+ *   pinned host memory   HOST-STAGED path (default): the batch owns a device staging arena and
+ *                        runs as 8 independent lanes (internal streams), each H2D -> Send kernel
+ *                        or Recv kernel -> D2H, so the copy engines and the SMs overlap; a
+ *                        connection always maps to the same lane, which keeps its Send and Recv
+ *                        ordered.  With a NULL stream the lanes run free (b200_lanes_join or
+ *                        b200_batch_results to wait); with a stream the batch forks from / joins
+ *                        back into it.  B200_BATCH_ZEROCOPY instead lets the kernels read and
+ *                        write the pinned buffers directly (GPUDirect-style, no staging).
+ */
 
 typedef struct b200_send_op {
   b200_pair* pair;
@@ -216,6 +229,10 @@ b200_batch* b200_batch_prepare_recv(const b200_recv_op* ops, size_t nops, int fl
 int b200_batch_launch(b200_batch* b, void* stream);       /* asynchronous */
 /* Per-op byte counts of the most recent launch (synchronises the stream). */
 int b200_batch_results(b200_batch* b, uint64_t* out, void* stream);
+/* Lanes of the host-staged path: make them wait for `stream` / make `stream` (or, with NULL,
+ * the calling thread) wait for them. */
+int b200_lanes_fork(void* stream);
+int b200_lanes_join(void* stream);
 /* Per-op number of Send / Recv calls that moved bytes, as fetched by the last
  * b200_batch_results (parity with the endpoint loops' iteration counts). */
 int b200_batch_calls(b200_batch* b, uint64_t* out);

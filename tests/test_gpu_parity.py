@@ -245,12 +245,13 @@ def test_poller_scan_and_eventfd(gpu):
         a.disconnect(); b.disconnect(); a.putback(); b.putback()
 
 
-def test_unprepared_batch_entry_points(gpu, oracle):
+@pytest.mark.parametrize("extra", [0, 4])   # 0: host-staged lanes, 4: B200_BATCH_ZEROCOPY
+def test_unprepared_batch_entry_points(gpu, oracle, extra):
     pkg, L = gpu, gpu.lib()
     pkg.config_set("B200_RING_BUFFER_SIZE_BYTES", 65536)
-    n = 6
+    n = 21
     pairs = [pkg.connected_pair("ub-a%d" % i, "ub-b%d" % i) for i in range(n)]
-    lens = [9, 3000, 9, 17]
+    lens = [9, 3000, 9, 17, 0, 20000]
     total = sum(lens)
     hsrc = L.b200_mem_alloc_host(n * total)
     hdst = L.b200_mem_alloc_host(n * total)
@@ -271,11 +272,27 @@ def test_unprepared_batch_entry_points(gpu, oracle):
         sops[i].pair, sops[i].slices, sops[i].nslices, sops[i].byte_idx = pairs[i][0].h, arr, len(lens), 0
         rops[i].pair, rops[i].dst, rops[i].cap = pairs[i][1].h, hdst + i * total, total
     acc = (C.c_uint64 * n)()
-    assert L.b200_pairs_send(sops, n, pkg.UNTIL_BLOCKED, acc, None) == 0
-    assert list(acc) == [total] * n
-    assert L.b200_pairs_recv(rops, n, pkg.UNTIL_BLOCKED, acc, None) == 0
-    assert list(acc) == [total] * n
-    assert np.array_equal(src, dst)
+    # the zero-length slice stops every Send call in front of it (pair.cc:683-685)
+    first = sum(lens[:4])
+    assert L.b200_pairs_send(sops, n, pkg.UNTIL_BLOCKED | extra, acc, None) == 0
+    assert list(acc) == [first] * n
+    assert L.b200_pairs_recv(rops, n, pkg.UNTIL_BLOCKED | extra, acc, None) == 0
+    assert list(acc) == [first] * n
+    for i in range(n):
+        assert np.array_equal(src[i * total:i * total + first], dst[i * total:i * total + first])
+    # a second round without the blocker, results come back in the caller's op order
+    for i in range(n):
+        sl = pkg.make_slices([(hsrc + i * total + first, 1000 + i)])
+        keep.append(sl)
+        sops[i].slices, sops[i].nslices = sl, 1
+        rops[i].dst, rops[i].cap = hdst + i * total + first, 1000 + i
+    assert L.b200_pairs_send(sops, n, pkg.UNTIL_BLOCKED | extra, acc, None) == 0
+    assert list(acc) == [1000 + i for i in range(n)]
+    assert L.b200_pairs_recv(rops, n, pkg.UNTIL_BLOCKED | extra, acc, None) == 0
+    assert list(acc) == [1000 + i for i in range(n)]
+    for i in range(n):
+        a0 = i * total + first
+        assert np.array_equal(src[a0:a0 + 1000 + i], dst[a0:a0 + 1000 + i])
     L.b200_mem_free_host(hsrc)
     L.b200_mem_free_host(hdst)
     for a, b in pairs:
