@@ -128,8 +128,11 @@ struct Runtime {
   Config cfg;
   cudaStream_t stream = nullptr;       // single-call + setup stream
   cudaStream_t poll_stream = nullptr;  // readiness scans
-  cudaStream_t lane_streams[kLanes] = {};
-  cudaEvent_t lane_events[kLanes] = {};
+  // host-staged lanes: an "up" stream (H2D + Send kernel) and a "down" stream (Recv kernel + D2H)
+  // per lane, tied together by events only where the protocol has a real dependency
+  cudaStream_t lane_up[kLanes] = {}, lane_down[kLanes] = {};
+  cudaEvent_t send_done[kLanes] = {}, recv_done[kLanes] = {};
+  cudaEvent_t join_up[kLanes] = {}, join_down[kLanes] = {};
   cudaEvent_t fork_event = nullptr;
   PairDev* d_pairs = nullptr;
   PairMirror* h_mirrors = nullptr;  // pinned, mapped
@@ -240,8 +243,10 @@ extern "C" int b200_init(int device) {
   if (!CU_OK(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking))) return -1;
   if (!CU_OK(cudaStreamCreateWithFlags(&r.poll_stream, cudaStreamNonBlocking))) return -1;
   for (int i = 0; i < kLanes; i++) {
-    if (!CU_OK(cudaStreamCreateWithFlags(&r.lane_streams[i], cudaStreamNonBlocking))) return -1;
-    if (!CU_OK(cudaEventCreateWithFlags(&r.lane_events[i], cudaEventDisableTiming))) return -1;
+    if (!CU_OK(cudaStreamCreateWithFlags(&r.lane_up[i], cudaStreamNonBlocking))) return -1;
+    if (!CU_OK(cudaStreamCreateWithFlags(&r.lane_down[i], cudaStreamNonBlocking))) return -1;
+    for (cudaEvent_t* e : {&r.send_done[i], &r.recv_done[i], &r.join_up[i], &r.join_down[i]})
+      if (!CU_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming))) return -1;
   }
   if (!CU_OK(cudaEventCreateWithFlags(&r.fork_event, cudaEventDisableTiming))) return -1;
   if (!CU_OK(cudaMalloc(&r.d_pairs, sizeof(PairDev) * kMaxPairs))) return -1;
@@ -305,8 +310,9 @@ extern "C" void b200_shutdown(void) {
   cudaStreamDestroy(r.stream);
   cudaStreamDestroy(r.poll_stream);
   for (int i = 0; i < kLanes; i++) {
-    cudaStreamDestroy(r.lane_streams[i]);
-    cudaEventDestroy(r.lane_events[i]);
+    cudaStreamDestroy(r.lane_up[i]);
+    cudaStreamDestroy(r.lane_down[i]);
+    for (cudaEvent_t e : {r.send_done[i], r.recv_done[i], r.join_up[i], r.join_down[i]}) cudaEventDestroy(e);
   }
   cudaEventDestroy(r.fork_event);
   r.inited = false;
@@ -931,7 +937,9 @@ extern "C" int b200_lanes_fork(void* stream) {
   Runtime& r = R();
   if (!CU_OK(cudaEventRecord(r.fork_event, (cudaStream_t)stream))) return -1;
   for (int L = 0; L < kLanes; L++)
-    if (!CU_OK(cudaStreamWaitEvent(r.lane_streams[L], r.fork_event, 0))) return -1;
+    if (!CU_OK(cudaStreamWaitEvent(r.lane_up[L], r.fork_event, 0)) ||
+        !CU_OK(cudaStreamWaitEvent(r.lane_down[L], r.fork_event, 0)))
+      return -1;
   return 0;
 }
 
@@ -940,10 +948,12 @@ extern "C" int b200_lanes_join(void* stream) {
   Runtime& r = R();
   for (int L = 0; L < kLanes; L++) {
     if (stream) {
-      if (!CU_OK(cudaEventRecord(r.lane_events[L], r.lane_streams[L])) ||
-          !CU_OK(cudaStreamWaitEvent((cudaStream_t)stream, r.lane_events[L], 0)))
+      if (!CU_OK(cudaEventRecord(r.join_up[L], r.lane_up[L])) ||
+          !CU_OK(cudaEventRecord(r.join_down[L], r.lane_down[L])) ||
+          !CU_OK(cudaStreamWaitEvent((cudaStream_t)stream, r.join_up[L], 0)) ||
+          !CU_OK(cudaStreamWaitEvent((cudaStream_t)stream, r.join_down[L], 0)))
         return -1;
-    } else if (!CU_OK(cudaStreamSynchronize(r.lane_streams[L]))) {
+    } else if (!CU_OK(cudaStreamSynchronize(r.lane_up[L])) || !CU_OK(cudaStreamSynchronize(r.lane_down[L]))) {
       return -1;
     }
   }
@@ -961,19 +971,27 @@ extern "C" int b200_batch_launch(b200_batch* b, void* stream) {
     r.launches++;
     return CU_OK(cudaGetLastError()) ? 0 : -1;
   }
-  // host-staged: every lane is its own stream; a connection always maps to the same lane, so
-  // Send and Recv of one connection stay ordered while lanes overlap H2D, kernels and D2H
+  // Host-staged: per lane, Send = H2D of the slices then the kernel on the "up" stream, Recv =
+  // the kernel then D2H of the destinations on the "down" stream.  A connection always maps to
+  // the same lane.  Dependencies are the protocol's own: Recv after the Send kernels that wrote
+  // the ring, Send kernel (not its H2D) after the Recv kernels that returned credit -- so the
+  // two copy engines and the SMs run concurrently across lanes and across consecutive batches.
   if (stream && b200_lanes_fork(stream) != 0) return -1;
   for (int L = 0; L < kLanes; L++) {
     LanePlan& lp = b->lanes[L];
     if (lp.nops == 0) continue;
-    cudaStream_t s = r.lane_streams[L];
     if (b->kind == 0) {
+      cudaStream_t s = r.lane_up[L];
       for (const CopyRun& c : lp.copies)
         if (!CU_OK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyHostToDevice, s))) return -1;
+      if (!CU_OK(cudaStreamWaitEvent(s, r.recv_done[L], 0))) return -1;
       launch_send(r.d_pairs, (const SendOpDev*)b->d_ops + lp.first_op, b->d_results + lp.first_op, lp.nops, s);
+      if (!CU_OK(cudaEventRecord(r.send_done[L], s))) return -1;
     } else {
+      cudaStream_t s = r.lane_down[L];
+      if (!CU_OK(cudaStreamWaitEvent(s, r.send_done[L], 0))) return -1;
       launch_recv(r.d_pairs, (const RecvOpDev*)b->d_ops + lp.first_op, b->d_results + lp.first_op, lp.nops, s);
+      if (!CU_OK(cudaEventRecord(r.recv_done[L], s))) return -1;
       for (const CopyRun& c : lp.copies)
         if (!CU_OK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s))) return -1;
     }
@@ -991,7 +1009,9 @@ extern "C" int b200_batch_results(b200_batch* b, uint64_t* out, void* stream) {
   cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
   if (b->staged) {
     for (int L = 0; L < kLanes; L++)
-      if (b->lanes[L].nops && !CU_OK(cudaStreamSynchronize(r.lane_streams[L]))) return -1;
+      if (b->lanes[L].nops &&
+          (!CU_OK(cudaStreamSynchronize(r.lane_up[L])) || !CU_OK(cudaStreamSynchronize(r.lane_down[L]))))
+        return -1;
   }
   if (!CU_OK(cudaMemcpyAsync(b->h_results, b->d_results, sizeof(OpResult) * b->nops, cudaMemcpyDeviceToHost, s)) ||
       !CU_OK(cudaStreamSynchronize(s)))
