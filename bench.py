@@ -301,6 +301,13 @@ def main():
     recv_ach = conns * rx_alg / (recv_ms * 1e-3) / 1e9
     send_ach = conns * tx_alg / (send_ms * 1e-3) / 1e9
     dominant = ("k_recv", recv_ach, recv_ms) if recv_ms >= send_ms else ("k_send", send_ach, send_ms)
+    traffic = None
+    try:  # dram bytes per launch from the committed ncu --set full capture of this same workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if conns == CONNS and msg == MSG_BYTES:
+            traffic = tj[dominant[0]]["dram_bytes"]
+    except Exception:
+        pass
 
     # ---- e2e: host buffers, through the same C-ABI calls, copies inside the timed region
     e2e = None
@@ -330,7 +337,7 @@ def main():
                              "between steps" % (conns * total / 2**30, conns * args.ring_kb / 2**20),
                        "sharding": "connection c of rank r is independent; no data-path collective"},
             "roofline": {"bound": "hbm", "kernel": dominant[0], "achieved": dominant[1], "peak": peak,
-                         "unit": "GB/s", "frac": dominant[1] / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": dominant[1] / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": conns * (rx_alg if dominant[0] == "k_recv" else tx_alg),
                          "avg_launch_ms": dominant[2],
                          "kernels": {"k_send": {"ms": send_ms, "GBps": send_ach, "frac": send_ach / peak},

@@ -88,7 +88,7 @@ struct b200_pair {
   bool in_poller = false;
 };
 
-constexpr int kLanes = 8;  // internal streams of the host-staged path
+constexpr int kLanes = 16;  // max internal lanes of the host-staged path (B200_LANES, default 8)
 
 struct CopyRun {  // one cudaMemcpyAsync
   void* dst;
@@ -776,9 +776,11 @@ static int mem_class(const void* p) {
 }
 
 static int lane_of(const b200_pair* p) {
+  static const int nl = [] { long v = env_long("B200_LANES", 8); return (int)(v < 1 ? 1 : v > kLanes ? kLanes : v); }();
+  static const int shift = (int)env_long("B200_LANE_SHIFT", 1);
   int key = p->slot;
   if (p->peer_local && p->peer_local->slot < key) key = p->peer_local->slot;
-  return (key >> 1) % kLanes;  // both ends of a loopback connection share a lane: per-connection order
+  return (key >> shift) % nl;  // both ends of a loopback connection share a lane: per-connection order
 }
 
 static size_t stage_place(size_t& cursor, const void* host_ptr, size_t bytes) {
