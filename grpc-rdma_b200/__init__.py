@@ -19,6 +19,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.environ.get("B200RDMA_LIB") or os.path.join(PKG_DIR, "lib", "libb200rdma.so")  # env: experiment builds
 HEADER = os.path.join(ROOT, "include", "b200_pair.h")
+ENDPOINT_LIB_PATH = os.path.join(PKG_DIR, "lib", "libb200_endpoint.so")
+ENDPOINT_HEADER = os.path.join(ROOT, "include", "b200_endpoint.h")
 
 ADDRESS_BYTES = 48
 ONE_CALL, UNTIL_BLOCKED, ASYNC, ZEROCOPY = 0, 1, 2, 4
@@ -48,7 +50,7 @@ class PairState(C.Structure):
 
 def build(verbose=False):
     """Compile lib/libb200rdma.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    out = subprocess.run(["make", "-C", PKG_DIR], capture_output=True, text=True)
+    out = subprocess.run(["make", "-C", PKG_DIR, "all"], capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("building libb200rdma.so failed:\n" + out.stdout + out.stderr)
     if verbose:

@@ -1,0 +1,88 @@
+"""CPU: the product's endpoint state machine + BPEV hybrid poll loop (grpc-rdma_b200/host/
+b200_endpoint.cc) driven by the reference's endpoint conformance pattern
+(test/core/iomgr/endpoint_tests.cc) with the pair operations supplied by the CPU oracle through the
+b200_pair_ops table -- host logic only, no GPU, no CUDA calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import endpoint_lib
+
+
+@pytest.fixture(scope="module")
+def drv(pkg):
+    D, (O, ops) = endpoint_lib.load(pkg, need_oracle=True)
+    return D, O, ops
+
+
+def test_endpoint_library_exports_every_header_symbol(pkg):
+    if not os.path.exists(pkg.ENDPOINT_LIB_PATH):
+        pkg.build()
+    txt = re.sub(r"/\*.*?\*/", "", open(pkg.ENDPOINT_HEADER).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(b200_(?:engine|endpoint|exchange)[a-z0-9_]*)\s*\(", txt)))
+    assert len(syms) >= 14, syms
+    C.CDLL(pkg.LIB_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(pkg.ENDPOINT_LIB_PATH)
+    assert not [s for s in syms if not hasattr(L, s)]
+
+
+@pytest.mark.parametrize("ring", [4096, 65536])
+def test_read_and_write_8192_byte_slices(drv, ring):
+    D, O, ops = drv
+    O.oracle_ops_config(ring, 30)
+    st = (C.c_uint64 * 4)()
+    # endpoint_tests.cc:341 shape (10 MB / 100 kB writes / 8192-B slices), scaled to run in seconds
+    assert D.drv_read_and_write(ops, 2_000_000, 100_000, 8192, 0, 50, 0, st) == 0
+    assert st[0] > 0 and st[2] > 0  # the busy-poll scan synthesized the events
+
+
+def test_read_and_write_one_byte_slices(drv):
+    D, O, ops = drv
+    O.oracle_ops_config(65536, 30)
+    # :342 shape: every slice one byte -> one 24-byte ring frame per byte, <= max_sge per Send
+    assert D.drv_read_and_write(ops, 60_000, 10_000, 1, 0, 50, 0, None) == 0
+
+
+def test_read_and_write_with_shutdown(drv):
+    D, O, ops = drv
+    O.oracle_ops_config(65536, 30)
+    assert D.drv_read_and_write(ops, 10_000_000, 100_000, 1, 1, 50, 0, None) == 0  # :343
+
+
+def test_read_and_write_slice_size_sweep(drv):
+    D, O, ops = drv
+    O.oracle_ops_config(1024, 30)   # a ring smaller than one write: partial writes + credit returns
+    i = 1
+    while i < 1000:                 # :344-346
+        assert D.drv_read_and_write(ops, 40320, i, i, 0, 50, 0, None) == 0, i
+        i = max(i + 1, i * 5 // 4)
+
+
+def test_message_larger_than_ring_and_staging(drv):
+    D, O, ops = drv
+    O.oracle_ops_config(4096, 30)
+    assert D.drv_read_and_write(ops, 300_000, 300_000, 100_000, 0, 50, 0, None) == 0
+
+
+def test_shutdown_sequence(drv):
+    D, O, ops = drv
+    O.oracle_ops_config(4096, 30)
+    assert D.drv_shutdown_sequence(ops, 50) == 0
+
+
+def test_peer_close_fails_pending_read(drv):
+    D, O, ops = drv
+    O.oracle_ops_config(4096, 30)
+    assert D.drv_peer_close(ops, 50, 0) == 0
+
+
+def test_echo_random_messages(drv):
+    D, O, ops = drv
+    O.oracle_ops_config(65536, 30)
+    nbytes = C.c_uint64(0)
+    # examples/cpp/test: random messages, msg == reply; one thread, one engine (oracle wire is not
+    # thread-safe), sizes scaled to the small ring
+    assert D.drv_echo(ops, 40, 300_000, 12345, 50, 0, 0, C.byref(nbytes)) == 0
+    assert nbytes.value > 0
