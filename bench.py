@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stagger", type=int, default=0, help="1 = de-correlate the connections' ring positions first")
     return ap.parse_args()
 
 
@@ -238,6 +239,23 @@ def main():
         return pkg.Batch("send", sops, fl), pkg.Batch("recv", rops, fl), keep
 
     bs, br, keep = build_batches(src.data_ptr(), dst.data_ptr())
+    if args.stagger:
+        # connections of a real server are at uncorrelated ring positions; without this every ring of the
+        # job would sit at the same offset of its 16 MiB-aligned buffer on every step.  One preamble
+        # message of a connection-specific size (8 KiB .. 4 MiB) moves each cursor before anything is timed.
+        sops, rops, keep2 = [], [], []
+        for c in range(conns):
+            n = ((c * 40503 + 977 * rank) % 509 + 1) * 8192
+            arr = pkg.make_slices([(src.data_ptr() + c * total, n)])
+            keep2.append(arr)
+            sops.append((pairs[c][0], arr, 1, 0))
+            rops.append((pairs[c][1], dst.data_ptr() + c * total, n))
+        ps, pr = pkg.Batch("send", sops, pkg.UNTIL_BLOCKED), pkg.Batch("recv", rops, pkg.UNTIL_BLOCKED)
+        ps.launch(None)
+        pr.launch(None)
+        assert ps.results(None) == pr.results(None) == [((c * 40503 + 977 * rank) % 509 + 1) * 8192 for c in range(conns)]
+        ps.destroy()
+        pr.destroy()
     # an explicit stream: the library treats a NULL stream handle as "its own stream", and
     # torch.cuda.Event only sees the stream it is recorded on
     stream = torch.cuda.Stream(device=dev)
@@ -335,7 +353,9 @@ def main():
                        "connections_per_gpu": conns, "message_bytes": msg, "ring_kb": args.ring_kb,
                        "l2": "inputs larger than L2: %.2f GiB of slices + %.1f GiB of rings per GPU, no reuse "
                              "between steps" % (conns * total / 2**30, conns * args.ring_kb / 2**20),
-                       "sharding": "connection c of rank r is independent; no data-path collective"},
+                       "sharding": "connection c of rank r is independent; no data-path collective",
+                       "ring_positions": "staggered by one untimed preamble message per connection" if args.stagger
+                                         else "all connections at the same ring offset"},
             "roofline": {"bound": "hbm", "kernel": dominant[0], "achieved": dominant[1], "peak": peak,
                          "unit": "GB/s", "frac": dominant[1] / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": conns * (rx_alg if dominant[0] == "k_recv" else tx_alg),

@@ -12,14 +12,23 @@
 //                Poller::begin_polling poller.cc:66-101 and of the engine's
 //                busy-poll window ev_epollex_rdma_bpev_linux.cc:1104-1145)
 //
-// Pure indexing / memcpy work: HBM-bound, no tensor cores.  All bulk traffic is
-// 16-byte vector loads/stores; byte granularity only at the <16-byte edges of
-// a copy.  One CTA serves one (pair, op); inside the CTA, warp 0 does the
-// per-call integer planning with warp scans and all warps move bytes.
+// Pure indexing / memcpy work: HBM-bound, no tensor cores.  One CTA serves one
+// (pair, op): warp 0 runs the reference's integer logic with warp scans and
+// publishes 4 KiB work items; the mover warps pull every item's source bytes
+// into shared memory with the bulk-copy engine (cp.async.bulk + mbarrier
+// complete_tx, several stages in flight per warp, so the HBM read latency is
+// never held in registers) and write them out with aligned 16-byte vector
+// stores, re-aligning through a funnel shift when source and destination
+// differ mod 16 (gRPC slices sit at odd offsets, ring payloads at 8 mod 16).
+// Byte granularity only at the <16-byte edges of a copy.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "b200_dev.cuh"
+
+#ifndef B200_RECV_PROXY_FENCE
+#define B200_RECV_PROXY_FENCE 1
+#endif
 
 namespace b200 {
 
@@ -51,6 +60,12 @@ __device__ __forceinline__ uint64_t ld_acquire_u64(const void* p) {
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint64_t ld_volatile_u64(const void* p) {
+  uint64_t v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ uint32_t ld_acquire_u32(const void* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -62,115 +77,84 @@ __device__ __forceinline__ void st_release_v2u64(void* p, uint64_t a, uint64_t b
   asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
-// Take bytes [m, m+16) out of the 32-byte concatenation A|B (m = 1..15).
-template <bool kHi, bool kShift>
-__device__ __forceinline__ uint4 shift_window(uint4 A, uint4 B, unsigned sh) {
-  uint64_t a0 = (uint64_t)A.x | ((uint64_t)A.y << 32), a1 = (uint64_t)A.z | ((uint64_t)A.w << 32);
-  uint64_t b0 = (uint64_t)B.x | ((uint64_t)B.y << 32), b1 = (uint64_t)B.z | ((uint64_t)B.w << 32);
-  uint64_t w0 = kHi ? a1 : a0, w1 = kHi ? b0 : a1, w2 = kHi ? b1 : b0;
-  uint64_t lo, hi;
-  if (kShift) {
-    lo = (w0 >> sh) | (w1 << (64 - sh));
-    hi = (w1 >> sh) | (w2 << (64 - sh));
-  } else {
-    lo = w0;
-    hi = w1;
-  }
-  uint4 r;
-  r.x = (uint32_t)lo;
-  r.y = (uint32_t)(lo >> 32);
-  r.z = (uint32_t)hi;
-  r.w = (uint32_t)(hi >> 32);
-  return r;
+// ------------------------------------------------- bulk-copy engine (TMA) helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-
-template <bool kRingSrc>
-__device__ __forceinline__ uint4 ld_src16(const void* p) {
-  return kRingSrc ? ld_ring16(p) : ld_stream16(p);
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-
-constexpr int kUnroll = 8;  // 16-byte vectors in flight per lane: one 4 KiB work item = one block
-
-__device__ __forceinline__ uint4 shfl_down1_wrap(uint4 a, uint4 next0, uint32_t lane) {
-  // lane L gets lane L+1's vector; lane 31 gets lane 0's vector of the next row
-  uint4 t, w;
-  t.x = __shfl_down_sync(0xffffffffu, a.x, 1);
-  t.y = __shfl_down_sync(0xffffffffu, a.y, 1);
-  t.z = __shfl_down_sync(0xffffffffu, a.z, 1);
-  t.w = __shfl_down_sync(0xffffffffu, a.w, 1);
-  w.x = __shfl_sync(0xffffffffu, next0.x, 0);
-  w.y = __shfl_sync(0xffffffffu, next0.y, 0);
-  w.z = __shfl_sync(0xffffffffu, next0.z, 0);
-  w.w = __shfl_sync(0xffffffffu, next0.w, 0);
-  return lane == 31 ? w : t;
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
+// global -> shared, completion counted in bytes on `bar`.  dst, src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// order this thread's earlier generic-proxy observations of global memory before its bulk copies
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// Warp-cooperative: dst 16-byte aligned, src misaligned by m = src & 15 (1..15).  Output vector i
-// is cut out of aligned source vectors i and i+1; vector i+1 is the neighbour lane's load (shuffle),
-// so every source byte is fetched once and kUnroll loads per lane are in flight.  Source vector
-// `nvec` always contains a byte of the range (never faults); vectors beyond it are not touched.
-// One block = up to 32*kUnroll output vectors (4 KiB).  All kUnroll loads of a lane are in
-// flight at once; a short block is handled by predication, never by a slower loop.  Source
-// word w exists iff w <= nvec, output vector v exists iff v < nvec (nvec <= 32*kUnroll).
-template <bool kRingSrc, bool kHi, bool kShift>
-__device__ __noinline__ void copy_block_shifted(uint4* __restrict__ d, const uint4* __restrict__ s, uint32_t nvec,
-                                                unsigned sh, uint32_t lane) {
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  const uint4* sl = s + lane;
-  uint4* dl = d + lane;
-  uint4 A[kUnroll + 1];
-#pragma unroll
-  for (int k = 0; k <= kUnroll; k++) A[k] = (32u * k + lane <= nvec) ? ld_src16<kRingSrc>(sl + 32 * k) : zero;
-#pragma unroll
-  for (int k = 0; k < kUnroll; k++) {
-    const uint4 B = shfl_down1_wrap(A[k], A[k + 1], lane);
-    if (32u * k + lane < nvec) st_stream16(dl + 32 * k, shift_window<kHi, kShift>(A[k], B, sh));
+// Output vector i = source bytes [16 i + m, 16 i + m + 16) of the 16-byte aligned shared array
+// sv, m = 4 K + r/8.  Warp-cooperative, aligned 16-byte global stores.
+template <int K>
+__device__ __forceinline__ void s2g_vectors(uint4* __restrict__ dv, const uint4* __restrict__ sv, uint32_t nvec,
+                                            uint32_t r, uint32_t lane) {
+#pragma unroll 4
+  for (uint32_t i = lane; i < nvec; i += 32) {
+    const uint4 A = sv[i], B = sv[i + 1];
+    uint32_t x0, x1, x2, x3, x4;
+    if (K == 0) { x0 = A.x; x1 = A.y; x2 = A.z; x3 = A.w; x4 = B.x; }
+    else if (K == 1) { x0 = A.y; x1 = A.z; x2 = A.w; x3 = B.x; x4 = B.y; }
+    else if (K == 2) { x0 = A.z; x1 = A.w; x2 = B.x; x3 = B.y; x4 = B.z; }
+    else { x0 = A.w; x1 = B.x; x2 = B.y; x3 = B.z; x4 = B.w; }
+    uint4 o;
+    o.x = __funnelshift_r(x0, x1, r);
+    o.y = __funnelshift_r(x1, x2, r);
+    o.z = __funnelshift_r(x2, x3, r);
+    o.w = __funnelshift_r(x3, x4, r);
+    st_stream16(dv + i, o);
   }
 }
 
-template <bool kRingSrc>
-__device__ __noinline__ void copy_block_aligned(uint4* __restrict__ d, const uint4* __restrict__ s, uint32_t nvec,
-                                                uint32_t lane) {
-  const uint4* sl = s + lane;
-  uint4* dl = d + lane;
-  uint4 v[kUnroll];
-#pragma unroll
-  for (int k = 0; k < kUnroll; k++)
-    if (32u * k + lane < nvec) v[k] = ld_src16<kRingSrc>(sl + 32 * k);
-#pragma unroll
-  for (int k = 0; k < kUnroll; k++)
-    if (32u * k + lane < nvec) st_stream16(dl + 32 * k, v[k]);
-}
-
-// Warp-cooperative copy of n bytes, any alignment on either side.  Bulk = aligned 16-byte
-// stores; the <16-byte head and tail use one byte per lane.
-template <bool kRingSrc>
-__device__ __forceinline__ uint8_t ld_byte(const uint8_t* p) {
-  return kRingSrc ? *reinterpret_cast<const volatile uint8_t*>(p) : __ldg(p);
-}
-
-template <bool kRingSrc>
-__device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, uint64_t n, uint32_t lane) {
+// Warp-cooperative copy of n bytes from shared memory (16-byte aligned base `sbase`, byte offset
+// `soff`) to global memory at any alignment.  The stage holds at least one 16-byte block past the
+// last source byte's block start, so vector i+1 is always readable.
+__device__ __forceinline__ void smem_to_global(uint8_t* dst, const uint8_t* sbase, uint32_t soff, uint32_t n,
+                                               uint32_t lane) {
   if (n == 0) return;
-  uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+  uint32_t head = (16 - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
   if (head > n) head = n;
-  const uint64_t nvec = (n - head) >> 4;
-  const uint64_t tail = n - head - (nvec << 4);
-  // <16-byte edges: one byte per lane
-  if (lane < head) dst[lane] = ld_byte<kRingSrc>(src + lane);
-  if (lane < tail) dst[head + (nvec << 4) + lane] = ld_byte<kRingSrc>(src + head + (nvec << 4) + lane);
-  const uint8_t* vsrc = src + head;
-  const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(vsrc) & 15);
-  constexpr uint64_t kBlk = 32ull * kUnroll;
-  const unsigned sh = (m & 7) * 8;
-  const uint4* sal = reinterpret_cast<const uint4*>(vsrc - m);
+  const uint32_t nvec = (n - head) >> 4;
+  const uint32_t tail = n - head - (nvec << 4);
+  if (lane < head) dst[lane] = sbase[soff + lane];
+  if (lane < tail) dst[head + (nvec << 4) + lane] = sbase[soff + head + (nvec << 4) + lane];
+  const uint32_t vs = soff + head, m = vs & 15;
+  const uint4* sv = reinterpret_cast<const uint4*>(sbase + (vs - m));
   uint4* dv = reinterpret_cast<uint4*>(dst + head);
-  for (uint64_t v0 = 0; v0 < nvec; v0 += kBlk) {
-    const uint32_t nb = (uint32_t)(nvec - v0 < kBlk ? nvec - v0 : kBlk);
-    if (m == 0) copy_block_aligned<kRingSrc>(dv + v0, sal + v0, nb, lane);
-    else if (!(m & 8)) copy_block_shifted<kRingSrc, false, true>(dv + v0, sal + v0, nb, sh, lane);
-    else if (sh) copy_block_shifted<kRingSrc, true, true>(dv + v0, sal + v0, nb, sh, lane);
-    else copy_block_shifted<kRingSrc, true, false>(dv + v0, sal + v0, nb, sh, lane);
+  if (m == 0) {
+#pragma unroll 4
+    for (uint32_t i = lane; i < nvec; i += 32) st_stream16(dv + i, sv[i]);
+    return;
+  }
+  const uint32_t r = (m & 3) * 8;
+  switch (m >> 2) {
+    case 0: s2g_vectors<0>(dv, sv, nvec, r, lane); break;
+    case 1: s2g_vectors<1>(dv, sv, nvec, r, lane); break;
+    case 2: s2g_vectors<2>(dv, sv, nvec, r, lane); break;
+    default: s2g_vectors<3>(dv, sv, nvec, r, lane); break;
   }
 }
 
@@ -193,6 +177,7 @@ __device__ __forceinline__ void coop_zero(uint8_t* p, uint64_t n, uint32_t lane)
 // GetReadableSize / HasMessage of a pair whose cursor is (head, remain)
 // (ring_buffer.cc:56-97).  A header larger than cap-24 is a torn read in the
 // reference (it spins); here it reports "not readable yet".
+template <bool kSys = true>  // kSys: the ring may be written from outside this GPU (NIC, peer GPU)
 __device__ __forceinline__ void rx_probe(const uint8_t* ring, uint64_t cap, uint64_t head, uint64_t remain,
                                          uint32_t& has_msg, uint64_t& readable) {
   if (remain > 0) {
@@ -200,49 +185,71 @@ __device__ __forceinline__ void rx_probe(const uint8_t* ring, uint64_t cap, uint
     readable = remain;
     return;
   }
-  uint64_t hdr = ld_acquire_u64(ring + head);
+  uint64_t hdr = kSys ? ld_acquire_u64(ring + head) : ld_volatile_u64(ring + head);
   has_msg = hdr != 0;
   readable = 0;
   if (hdr != 0 && hdr <= cap - kReserved) {
-    uint64_t foot = ld_acquire_u64(ring + ((head + 8 + round_up8(hdr)) & (cap - 1)));
+    const uint8_t* fp = ring + ((head + 8 + round_up8(hdr)) & (cap - 1));
+    uint64_t foot = kSys ? ld_acquire_u64(fp) : ld_volatile_u64(fp);
     if (foot == kFooter) readable = hdr;
   }
 }
 
-__device__ __forceinline__ void publish_mirror(PairMirror* m, const PairDev* P, uint32_t has_msg,
-                                               uint64_t readable) {
+// Host-visible mirror (pinned, mapped): posted writes only -- a kernel never reads host memory.
+// The receive side and the send side of a pair may run concurrently (different streams), so each
+// publishes only the fields it owns.
+__device__ __forceinline__ void publish_mirror_rx(PairMirror* m, const PairDev* P, uint32_t has_msg,
+                                                  uint64_t readable) {
   if (m == nullptr) return;
   volatile PairMirror* vm = m;
   vm->head = P->head;
   vm->moving_head = P->moving_head;
   vm->remain = P->remain;
   vm->acc = P->acc;
+  vm->readable = readable;
+  vm->has_message = has_msg;
+}
+__device__ __forceinline__ void publish_mirror_tx(PairMirror* m, const PairDev* P) {
+  if (m == nullptr) return;
+  volatile PairMirror* vm = m;
   vm->remote_tail = P->remote_tail;
   vm->credit_head = P->credit_head;
-  vm->readable = readable;
   vm->partial_write = P->partial_write;
   vm->peer_exit = P->credit_exit;
-  vm->has_message = has_msg;
-  __threadfence_system();
-  vm->seq = vm->seq + 1;
 }
 
 // =========================================================================
-// Producer / consumer skeleton shared by k_send and k_recv
+// Producer / mover skeleton shared by k_send and k_recv
 // =========================================================================
 //
 // One CTA per (pair, op).  Warp 0 is the producer: it runs the reference's
-// integer logic (Send planning / frame-list walking) ahead of the data movers
-// and publishes 4 KiB work items into a ticket ring in shared memory.  All
-// other warps (and warp 0 once it has nothing left to publish) claim items from
-// a shared counter and move bytes.  There is no CTA barrier on the steady-state
-// path; a "segment" ends only where the protocol needs everything before it to
-// be finished: the footer flush of Send, the credit write of Recv, the end of
-// the op.
+// integer logic (Send planning / frame-list walking) ahead of the data and
+// publishes 4 KiB work items into a ticket ring in shared memory.  The other
+// warps are movers.  A mover owns kDepth private stages in shared memory: it
+// takes a ticket, starts the bulk copy of that item's source bytes into a free
+// stage (completion counted on the stage's mbarrier) and only then turns to its
+// oldest landed stage and writes it out, so every mover keeps up to kDepth x
+// 4 KiB of HBM reads in flight without holding them in registers.  There is no
+// CTA barrier on the steady-state path; a "segment" ends only where the
+// protocol needs everything before it to be finished: the footer flush of Send,
+// the credit write of Recv, the end of the op.
 
-constexpr int kThreads = 512;
-constexpr uint32_t kChunk = 4096;  // payload bytes per work item
-constexpr uint32_t kQI = 256;      // ticket ring entries (1 MiB of look-ahead)
+#ifndef B200_MOVERS
+#define B200_MOVERS 8
+#endif
+#ifndef B200_DEPTH
+#define B200_DEPTH 3
+#endif
+#ifndef B200_CHUNK
+#define B200_CHUNK 4096
+#endif
+constexpr int kMovers = B200_MOVERS;            // mover warps per CTA
+constexpr int kThreads = 32 * (1 + kMovers);    // + the producer warp
+constexpr int kDepth = B200_DEPTH;                     // stages (bulk copies in flight) per mover warp
+constexpr uint32_t kChunk = B200_CHUNK;             // payload bytes per work item
+constexpr uint32_t kStageBytes = kChunk + 32;   // + up to 15 bytes of alignment slack on either side
+constexpr uint32_t kStageTotal = kMovers * kDepth * kStageBytes;  // dynamic shared memory per CTA
+constexpr uint32_t kQI = 128;                   // ticket ring entries (descriptor look-ahead)
 
 struct WorkItem {      // 32 bytes
   uint64_t a;          // send: source pointer          recv: ring offset of the payload bytes
@@ -274,46 +281,86 @@ __device__ __forceinline__ void publish_item(WorkItem* q, uint32_t id, uint64_t 
   *(volatile uint32_t*)&slot->ready = id + 1;
 }
 
-// consumer side: claim the next item; false when the segment is drained
-__device__ __forceinline__ bool claim_item(WorkItem* q, PipeCtl* ctl, uint32_t lane, uint64_t& a, uint64_t& b,
-                                           uint64_t& c, uint32_t& n) {
-  uint32_t w = 0;
-  if (lane == 0) w = atomicAdd(&ctl->next, 1u);
-  w = __shfl_sync(0xffffffffu, w, 0);
-  WorkItem* slot = &q[w % kQI];
-  bool got = false;
+__device__ __forceinline__ void movers_init(uint64_t* bars, uint32_t tid) {
+  if (tid < kMovers * kDepth) mbar_init(&bars[tid], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Mover warp, one segment.  Move::issue (lane 0) starts the bulk copy of an item into a stage;
+// Move::process (whole warp) writes a landed stage out.  The item's descriptor stays in its
+// ticket-ring slot until it has been written out; the next ticket is always claimed ahead of
+// time so that a freed stage is refilled without waiting for the shared counter.  phase_bits
+// carries the stages' mbarrier parities from segment to segment.
+template <class Move>
+__device__ __forceinline__ void mover_run(const Move& mv, WorkItem* q, PipeCtl* ctl, uint8_t* stages, uint64_t* bars,
+                                          uint32_t& phase_bits, uint32_t lane) {
+  static_assert(kQI <= 256 && kDepth <= 8, "slot_of packs one byte per stage");
+  uint32_t head = 0, tail = 0, ticket = 0;
+  uint64_t slot_of = 0;  // ticket-ring slot of the item in stage s, one byte per stage
+  bool drained = false;
+  if (lane == 0) ticket = atomicAdd(&ctl->next, 1u);
   while (true) {
-    if (ld_shared_volatile(&slot->ready) == w + 1) {
-      got = true;
-      break;
+    // ---- fill: start copies into free stages while published items are available
+    while (!drained && tail - head < (uint32_t)kDepth) {
+      uint32_t st = 0;  // 0 = ticket not published yet, 1 = copy started, 2 = segment drained
+      if (lane == 0) {
+        const uint32_t si = ticket % kQI;
+        WorkItem* slot = &q[si];
+        if (ld_shared_volatile(&slot->ready) == ticket + 1) {
+          st = 1;
+        } else if (ld_shared_volatile(&ctl->seg_done) && ticket >= ld_shared_volatile(&ctl->total_items)) {
+          st = ld_shared_volatile(&slot->ready) == ticket + 1 ? 1 : 2;  // re-check: published in between?
+        }
+        if (st == 1) {
+          __threadfence_block();
+          const uint32_t s = tail % kDepth;
+          mv.issue(slot->a, slot->n, stages + s * kStageBytes, &bars[s]);
+          st |= si << 8;
+          ticket = atomicAdd(&ctl->next, 1u);  // claim ahead
+        }
+      }
+      st = __shfl_sync(0xffffffffu, st, 0);
+      if ((st & 3) == 1) {
+        const uint32_t sh = 8 * (tail % kDepth);
+        slot_of = (slot_of & ~(0xffull << sh)) | ((uint64_t)(st >> 8) << sh);
+        tail++;
+      } else {
+        drained = (st & 3) == 2;
+        break;
+      }
     }
-    if (ld_shared_volatile(&ctl->seg_done) && w >= ld_shared_volatile(&ctl->total_items)) {
-      // re-check: the item may have been published between the two reads
-      got = ld_shared_volatile(&slot->ready) == w + 1;
-      break;
+    __syncwarp();
+    if (head == tail) {
+      if (drained) break;
+      __nanosleep(32);
+      continue;
     }
-    __nanosleep(40);
+    // ---- write out the oldest stage
+    const uint32_t s = head % kDepth;
+    const uint32_t par = (phase_bits >> s) & 1u;
+    while (!mbar_try_wait(&bars[s], par)) {
+    }
+    phase_bits ^= 1u << s;
+    WorkItem* w = &q[(uint32_t)(slot_of >> (8 * s)) & 0xffu];
+    const uint64_t ia = w->a, ib = w->b, ic = w->c;
+    const uint32_t in = w->n;
+    mv.process(ia, ib, ic, in, stages + s * kStageBytes, lane);
+    __syncwarp();  // every lane is done with the stage and the descriptor before they are reused
+    if (lane == 0) *(volatile uint32_t*)&w->ready = 0;  // the ticket-ring slot may be refilled
+    head++;
   }
-  got = __any_sync(0xffffffffu, got);
-  if (!got) return false;
-  __threadfence_block();
-  a = slot->a;
-  b = slot->b;
-  c = slot->c;
-  n = slot->n;
-  __syncwarp();
-  if (lane == 0) *(volatile uint32_t*)&slot->ready = 0;  // slot may be refilled
-  return true;
 }
 
 // =========================================================================
 // k_send
 // =========================================================================
 
-constexpr uint32_t kFootCap = 2048;  // footers buffered per segment (ring offsets / 8)
+constexpr uint32_t kTiny = 32;      // frames up to this size bypass the movers
+constexpr uint32_t kFootCap = 1024;  // footers buffered per segment (ring offsets / 8)
 
 struct SendPlanState {  // producer-only
-  uint64_t rt, cap, staging, total_left, written_total, ncalls, cur, bidx;
+  uint64_t rt, cap, staging, total_left, written_total, ncalls, cur, bidx, last_rh;
   uint32_t partial, max_sge;
 };
 
@@ -326,15 +373,22 @@ struct SendCallScratch {  // frames of the call being published
 
 // Producer: plan PairPollable::Send calls (pair.cc:645-734) one after another and publish
 // their frames as work items until the op is finished or the footer buffer is full.
-__device__ __noinline__ void send_produce_segment(const SendOpDev& op, const PairDev* P, SendPlanState& S,
-                                                  SendCallScratch& CS, WorkItem* q, PipeCtl* ctl, uint32_t* foot8,
-                                                  uint32_t* nfoot_out, uint32_t lane) {
+__device__ __noinline__ void send_produce_segment(const SendOpDev& op, const PairDev* P, uint8_t* ring,
+                                                  SendPlanState& S, SendCallScratch& CS, WorkItem* q, PipeCtl* ctl,
+                                                  uint32_t* foot8, uint32_t* nfoot_out, uint32_t lane) {
   const uint64_t cap = S.cap, mask = cap - 1;
   uint32_t base_item = 0, nfoot = 0;
   bool op_done = false;
   while (nfoot + kMaxSgeLimit <= kFootCap) {
     const uint64_t rt = S.rt;
-    const uint64_t rh = ld_acquire_u64(&P->credit_head);  // credit snapshot, once per call (pair.cc:650)
+    // credit snapshot, once per call (pair.cc:650).  The receiver publishes new credit with a
+    // system-scope release after zeroing the space; the matching acquire is only needed when the
+    // value moved, i.e. when this call may write into space that was just cleared.
+    const uint64_t rh = ld_volatile_u64(&P->credit_head);
+    if (rh != S.last_rh) {
+      __threadfence_system();
+      S.last_rh = rh;  // every lane writes the same value
+    }
     const uint64_t cur = S.cur, bidx = S.bidx;
     const uint64_t idx = cur + lane;
     const bool valid = lane < S.max_sge && idx < op.nslices;
@@ -367,7 +421,11 @@ __device__ __noinline__ void send_produce_segment(const SendOpDev& op, const Pai
     const unsigned fmask = __ballot_sync(0xffffffffu, p != 0);
     const uint32_t nframes = __popc(fmask);  // frames are lanes 0..nframes-1
     uint64_t wsum = p, esum = p ? encoded_size(p) : 0;
-    const uint32_t items = p ? (uint32_t)((p + kChunk - 1) / kChunk) : 0;
+    // Frames of <= kTiny bytes (chttp2's 9-byte DATA frame headers are every other slice) are
+    // written by the planner lane itself: they would otherwise occupy a mover stage for a full
+    // trip to memory each.
+    const bool tiny = p != 0 && p <= kTiny;
+    const uint32_t items = (p && !tiny) ? (uint32_t)((p + kChunk - 1) / kChunk) : 0;
     uint32_t items_incl = items;
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(0xffffffffu, items_incl, o);
@@ -387,6 +445,19 @@ __device__ __noinline__ void send_produce_segment(const SendOpDev& op, const Pai
       CS.off[lane] = foff;
       foot8[nfoot + lane] = (uint32_t)(((foff + 8 + round_up8(p)) & mask) >> 3);
     }
+    if (tiny) {
+      uint64_t w[kTiny / 8];
+#pragma unroll
+      for (int k = 0; k < (int)(kTiny / 8); k++) w[k] = 0;
+#pragma unroll
+      for (int i = 0; i < (int)kTiny; i++)
+        if ((uint64_t)i < p) w[i >> 3] |= (uint64_t)__ldg(ptr + i) << (8 * (i & 7));
+      *reinterpret_cast<uint64_t*>(ring + foff) = p;  // AppendHeader
+      // payload words (8-byte aligned in the ring; pad bytes are never delivered)
+#pragma unroll
+      for (int k = 0; k < (int)(kTiny / 8); k++)
+        if ((uint64_t)(8 * k) < p) *reinterpret_cast<uint64_t*>(ring + ((foff + 8 + 8 * k) & mask)) = w[k];
+    }
     if (lane == 0) {
       CS.first_item[32] = nitems;
       S.rt = (rt + esum) & mask;
@@ -403,6 +474,20 @@ __device__ __noinline__ void send_produce_segment(const SendOpDev& op, const Pai
     }
     __syncwarp();
     nfoot += nframes;
+    const unsigned big = __ballot_sync(0xffffffffu, items > 8);
+    if (!big && nitems <= kQI) {
+      // frame-parallel: lane f publishes the chunks of its own frame straight from registers.
+      // (nitems <= kQI: no lane can wait for a ticket-ring slot that an item of this same call
+      // still has to vacate.)
+      const uint32_t first = items_incl - items;
+      for (uint32_t t = 0; t < items; t++) {
+        const uint64_t c0 = (uint64_t)t * kChunk;
+        uint64_t n = p - c0;
+        if (n > kChunk) n = kChunk;
+        publish_item(q, base_item + first + t, reinterpret_cast<uint64_t>(ptr + c0), (foff + 8 + c0) & mask,
+                     c0 == 0 ? p : 0, (uint32_t)n);
+      }
+    } else
     // publish this call's items in id order, 32 at a time
     for (uint32_t it = lane; it < nitems; it += 32) {
       uint32_t f = 0;
@@ -432,10 +517,33 @@ __device__ __noinline__ void send_produce_segment(const SendOpDev& op, const Pai
   __syncwarp();
 }
 
+// Send mover: source = a slice at any alignment (linear), destination = the peer ring (may wrap).
+struct SendMove {
+  uint8_t* ring;
+  uint64_t cap, mask;
+  __device__ __forceinline__ void issue(uint64_t a, uint32_t n, uint8_t* stage, uint64_t* bar) const {
+    const uint32_t pre = (uint32_t)(a & 15);
+    const uint32_t len = (pre + n + 15u) & ~15u;  // the aligned 16-byte blocks that cover the chunk
+    mbar_expect_tx(bar, len);
+    bulk_g2s(stage, reinterpret_cast<const void*>(a - pre), len, bar);
+  }
+  __device__ __forceinline__ void process(uint64_t a, uint64_t b, uint64_t c, uint32_t n, const uint8_t* stage,
+                                          uint32_t lane) const {
+    const uint32_t pre = (uint32_t)(a & 15);
+    if (c != 0 && lane == 0) *reinterpret_cast<uint64_t*>(ring + ((b + cap - 8) & mask)) = c;  // AppendHeader
+    uint64_t seg1 = cap - b;
+    if (seg1 > n) seg1 = n;
+    smem_to_global(ring + b, stage, pre, (uint32_t)seg1, lane);
+    if (n > seg1) smem_to_global(ring, stage, pre + (uint32_t)seg1, n - (uint32_t)seg1, lane);  // wrap: WR1 at remote+0
+  }
+};
+
 __global__ void __launch_bounds__(kThreads, 2)
 k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult* __restrict__ results) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
   __shared__ WorkItem q[kQI];
   __shared__ PipeCtl ctl;
+  __shared__ uint64_t bars[kMovers * kDepth];
   __shared__ SendPlanState PS;
   __shared__ SendCallScratch CS;
   __shared__ uint32_t foot8[kFootCap];
@@ -447,6 +555,8 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid < kQI) q[tid].ready = 0;
+  movers_init(bars, tid);
+  uint32_t phase_bits = 0;
   if (tid == 0) {
     s_total = 0;
     s_status = P->status;
@@ -459,6 +569,7 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
     PS.written_total = 0;
     PS.ncalls = 0;
     PS.partial = P->partial_write;
+    PS.last_rh = ~0ull;  // not a ring offset: the first call always fences
   }
   __syncthreads();
   {  // total_slice_size, pair.cc:661-664
@@ -489,17 +600,11 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
       s_nfoot = 0;
     }
     __syncthreads();
-    if (warp == 0) send_produce_segment(op, P, PS, CS, q, &ctl, foot8, &s_nfoot, lane);
-    // ---------------------------------------------- move bytes
-    uint64_t a, b, c;
-    uint32_t n;
-    while (claim_item(q, &ctl, lane, a, b, c, n)) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(a);
-      if (c != 0 && lane == 0) *reinterpret_cast<uint64_t*>(ring + ((b + cap - 8) & mask)) = c;  // AppendHeader
-      uint64_t seg1 = cap - b;
-      if (seg1 > n) seg1 = n;
-      coop_copy<false>(ring + b, src, seg1, lane);
-      if (n > seg1) coop_copy<false>(ring, src + seg1, n - seg1, lane);  // wrap: WR1 at remote+0
+    if (warp == 0) {
+      send_produce_segment(op, P, ring, PS, CS, q, &ctl, foot8, &s_nfoot, lane);
+    } else {  // ---------------------------------------------- move bytes
+      const SendMove mv{ring, cap, mask};
+      mover_run(mv, q, &ctl, stage_mem + (warp - 1) * (kDepth * kStageBytes), &bars[(warp - 1) * kDepth], phase_bits, lane);
     }
     // footers last: a frame is complete for the reader only when header != 0 and footer == ~0
     // (ring_buffer.cc:75-96), so everything else of the segment is made visible first
@@ -518,21 +623,17 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
     P->partial_write = PS.partial;
     results[blockIdx.x].bytes = PS.written_total;
     results[blockIdx.x].calls = PS.ncalls;
-    publish_mirror(P->mirror, P, P->mirror ? ((volatile PairMirror*)P->mirror)->has_message : 0,
-                   P->mirror ? ((volatile PairMirror*)P->mirror)->readable : 0);
+    publish_mirror_tx(P->mirror, P);
     // loopback wire: the peer lives in this table, refresh its readiness hint
     if (P->peer_slot >= 0 && PS.written_total) {
-      __threadfence();
       PairDev* Q = &pairs[P->peer_slot];
-      uint32_t hm;
-      uint64_t rd;
-      rx_probe(Q->ring, Q->cap, *(volatile uint64_t*)&Q->head, *(volatile uint64_t*)&Q->remain, hm, rd);
       if (Q->mirror) {
+        uint32_t hm;
+        uint64_t rd;
+        rx_probe<false>(Q->ring, Q->cap, *(volatile uint64_t*)&Q->head, *(volatile uint64_t*)&Q->remain, hm, rd);
         volatile PairMirror* vm = Q->mirror;
         vm->has_message = hm;
         vm->readable = rd;
-        __threadfence_system();
-        vm->seq = vm->seq + 1;
       }
     }
   }
@@ -556,12 +657,6 @@ struct ScoutState {  // producer-only, lives in shared memory between segments
   uint64_t credit_val;
   uint32_t credit_flag;
 };
-
-__device__ __forceinline__ uint64_t ld_volatile_u64(const void* p) {
-  uint64_t v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // Producer: RingBufferPollable::Read (ring_buffer.cc:122-191) + PairPollable::Recv's credit
 // rule (pair.cc:276-284) as integer logic over the frame list.  Two steps per batch of <= 32
@@ -603,30 +698,74 @@ __device__ __noinline__ void recv_produce_segment(const RecvOpDev& op, const uin
     return __shfl_sync(0xffffffffu, win, (int)(d >> 3));
   };
   const bool one_call = !(op.flags & kFlagUntilBlocked);
+  // Frame streams are usually periodic with period two (chttp2: a 9-byte DATA header frame, then
+  // its payload frame), so once two consecutive frame sizes are known the next 32 frames can be
+  // checked speculatively: every lane loads the header at the position the pattern predicts, the
+  // positions are exact up to (and including) the first lane whose size breaks the pattern, and
+  // the footers of those lanes are loaded in a second parallel round -- two trips to memory per
+  // batch instead of one or two per frame.  pstate: 0 = sizes unknown (walk two frames), 1 = predict,
+  // 2 = the prediction just failed early (walk a full batch, predict again only if it shows period two).
+  uint32_t pstate = 0;
+  uint64_t pe1 = 0, pe2 = 0;  // encoded sizes of the last processed frame and of the one before
   while (true) {
-    // ---- step 1: walk the list; lane i keeps frame i
+    // ---- step 1: find up to 32 complete frames; lane i keeps frame i
     uint64_t my_r = 0, my_head = 0;
     bool my_open = false;
     uint32_t cnt = 0;
-    bool stopped = false;
+    bool stopped = false, predicted = false;
     uint64_t h = head;
     if (remain > 0) {  // rest of a partially consumed frame (its header is already cleared)
       if (lane == 0) my_r = remain;
       cnt = 1;
     }
-    const uint32_t want = one_call ? 1u : 32u;
-    while (cnt < want) {  // GetReadableSize, ring_buffer.cc:67-97
-      const uint64_t hdr = peek(h);
-      if (hdr == 0 || hdr > cap - kReserved) { stopped = true; break; }
-      const uint64_t foot = peek((h + 8 + round_up8(hdr)) & mask);
-      if (foot != kFooter) { stopped = true; break; }
-      if (lane == cnt) {
+    if (!one_call && pstate == 1) {
+      predicted = true;
+      const uint32_t c0 = cnt;
+      const uint32_t j = lane - c0;  // frame index after the cursor (lanes >= c0)
+      const uint64_t pred_e = (j & 1) ? pe1 : pe2;
+      const uint64_t rel = (uint64_t)(j >> 1) * (pe1 + pe2) + ((j & 1) ? pe2 : 0);
+      const bool mine = lane >= c0 && rel + pred_e <= cap;  // a genuine chain never laps the ring
+      const uint64_t off = (h + rel) & mask;
+      uint64_t hdr = 0;
+      if (mine) hdr = ld_volatile_u64(ring + off);
+      const uint64_t e = 16 + round_up8(hdr);
+      const bool valid = mine && hdr != 0 && hdr <= cap - kReserved && rel + e <= cap;
+      const unsigned mism = __ballot_sync(0xffffffffu, lane >= c0 && !(valid && e == pred_e));
+      const uint32_t k = mism ? (uint32_t)__ffs(mism) - 1 : 32u;  // first lane off the pattern: its position is still exact
+      uint64_t foot = 0;
+      if (valid && lane <= k) foot = ld_volatile_u64(ring + ((off + 8 + round_up8(hdr)) & mask));
+      const bool complete = valid && lane <= k && foot == kFooter;  // GetReadableSize, ring_buffer.cc:67-97
+      const unsigned inc = __ballot_sync(0xffffffffu, lane >= c0 && !complete);
+      const uint32_t stop_lane = inc ? (uint32_t)__ffs(inc) - 1 : 32u;
+      if (lane >= c0 && lane < stop_lane) {
         my_r = hdr;
-        my_head = h;
+        my_head = off;
         my_open = true;
       }
-      h = (h + 16 + round_up8(hdr)) & mask;
-      cnt++;
+      // the walk ends at a position known exactly whose frame is absent or incomplete: nothing more to read
+      stopped = stop_lane < 32 && stop_lane <= k && ((__ballot_sync(0xffffffffu, mine) >> stop_lane) & 1u);
+      cnt = stop_lane;
+      if (cnt > c0) {
+        const uint64_t off_l = __shfl_sync(0xffffffffu, off, cnt - 1);
+        const uint64_t e_l = __shfl_sync(0xffffffffu, e, cnt - 1);
+        h = (off_l + e_l) & mask;
+      }
+      if (!stopped && cnt - c0 < 4) pstate = 2;
+    } else {
+      const uint32_t want = one_call ? 1u : (pstate == 0 ? cnt + 2u : 32u);
+      while (cnt < want) {  // GetReadableSize, ring_buffer.cc:67-97
+        const uint64_t hdr = peek(h);
+        if (hdr == 0 || hdr > cap - kReserved) { stopped = true; break; }
+        const uint64_t foot = peek((h + 8 + round_up8(hdr)) & mask);
+        if (foot != kFooter) { stopped = true; break; }
+        if (lane == cnt) {
+          my_r = hdr;
+          my_head = h;
+          my_open = true;
+        }
+        h = (h + 16 + round_up8(hdr)) & mask;
+        cnt++;
+      }
     }
     // ---- step 2: Read()/Recv() per frame, all lanes at once
     const bool valid = lane < cnt;
@@ -676,7 +815,23 @@ __device__ __noinline__ void recv_produce_segment(const RecvOpDev& op, const uin
       break;
     }
     const bool proc2 = lane < nproc;
-    const uint32_t items = proc2 ? (uint32_t)((n + kChunk - 1) / kChunk) : 0;
+    // A whole frame of <= kTiny bytes is delivered and retired by its own lane (the words were
+    // just read by the walk, so they come from L2): ring_buffer.cc:146-183 for one small frame.
+    const bool tiny = proc2 && my_open && n == my_r && n <= kTiny;
+    if (tiny) {
+      uint64_t w[kTiny / 8];
+#pragma unroll
+      for (int k = 0; k < (int)(kTiny / 8); k++)
+        w[k] = (uint64_t)(8 * k) < n ? ld_volatile_u64(ring + ((my_head + 8 + 8 * k) & mask)) : 0;
+      uint8_t* d = op.dst + delivered + r_excl;
+#pragma unroll
+      for (int i = 0; i < (int)kTiny; i++)
+        if ((uint64_t)i < n) d[i] = (uint8_t)(w[i >> 3] >> (8 * (i & 7)));
+      uint8_t* wr = const_cast<uint8_t*>(ring);
+      const uint32_t nw = (uint32_t)(round_up8(n) >> 3) + 2;  // header + payload words + footer
+      for (uint32_t k = 0; k < nw; k++) *reinterpret_cast<uint64_t*>(wr + ((my_head + 8 * k) & mask)) = 0;
+    }
+    const uint32_t items = (proc2 && !tiny) ? (uint32_t)((n + kChunk - 1) / kChunk) : 0;
     uint32_t items_incl = items;
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(0xffffffffu, items_incl, o);
@@ -727,6 +882,27 @@ __device__ __noinline__ void recv_produce_segment(const RecvOpDev& op, const uin
     ncalls += nproc;
     if (one_call || cap_left == 0 || (stopped && nproc == cnt)) last = 1;
     if (last || credit) break;
+    {  // pattern for the next batch: the encoded sizes of the last two frames processed
+      const bool two = L >= 1 && __shfl_sync(0xffffffffu, (int)my_open, L - (L >= 1 ? 1 : 0)) != 0 && open_L && remain == 0;
+      if (two) {
+        const uint64_t ra = r_L, rb = __shfl_sync(0xffffffffu, my_r, L - 1);
+        const uint64_t na = 16 + round_up8(ra), nb = 16 + round_up8(rb);
+        bool ok = true;
+        if (pstate == 2 && !predicted) {  // distrust: the window walk must itself show period two
+          ok = false;
+          if (L >= 3) {
+            const uint64_t rc = __shfl_sync(0xffffffffu, my_r, L - 2), rd = __shfl_sync(0xffffffffu, my_r, L - 3);
+            const bool oc = __shfl_sync(0xffffffffu, (int)my_open, L - 3) != 0;
+            ok = oc && round_up8(rc) == round_up8(ra) && round_up8(rd) == round_up8(rb);
+          }
+        }
+        pe1 = na;
+        pe2 = nb;
+        if (pstate == 0 || (pstate == 2 && !predicted && ok)) pstate = 1;
+      } else if (pstate == 1) {
+        pstate = 0;
+      }
+    }
   }
   if (lane == 0) {
     SS.head = head;
@@ -746,10 +922,52 @@ __device__ __noinline__ void recv_produce_segment(const RecvOpDev& op, const uin
   __syncwarp();
 }
 
+// Recv mover: source = ring bytes (may wrap), destination = the caller's slice (linear);
+// everything the item retires is zeroed once its bytes have landed in shared memory.
+struct RecvMove {
+  uint8_t* ring;
+  uint8_t* dst;
+  uint64_t cap, mask;
+  __device__ __forceinline__ void issue(uint64_t a, uint32_t n, uint8_t* stage, uint64_t* bar) const {
+    const uint32_t pre = (uint32_t)(a & 15);
+    const uint64_t start = a - pre;
+#if B200_RECV_PROXY_FENCE
+    fence_proxy_async_global();  // the frame was validated with generic loads; the copy reads through the async proxy
+#endif
+    if (a + n <= cap) {
+      const uint32_t len = (pre + n + 15u) & ~15u;
+      mbar_expect_tx(bar, len);
+      bulk_g2s(stage, ring + start, len, bar);
+    } else {  // the chunk crosses the ring end: two copies, contiguous in the stage
+      const uint32_t len1 = (uint32_t)(cap - start);  // multiple of 16 (cap is a power of two >= 16)
+      const uint32_t n2 = n - (uint32_t)(cap - a);
+      const uint32_t len2 = (n2 + 15u) & ~15u;
+      mbar_expect_tx(bar, len1 + len2);
+      bulk_g2s(stage, ring + start, len1, bar);
+      bulk_g2s(stage + len1, ring, len2, bar);
+    }
+  }
+  __device__ __forceinline__ void process(uint64_t a, uint64_t b, uint64_t c, uint32_t n, const uint8_t* stage,
+                                          uint32_t lane) const {
+    // ---- clear-on-read: exactly what the item retired (its bytes are already in shared memory)
+    const uint32_t zhead = (uint32_t)(c & 0xffff), ztail = (uint32_t)(c >> 16);
+    const uint64_t zs = (a + cap - zhead) & mask;
+    const uint64_t zl = (uint64_t)zhead + n + ztail;
+    uint64_t z1 = cap - zs;
+    if (z1 > zl) z1 = zl;
+    coop_zero(ring + zs, z1, lane);
+    if (zl > z1) coop_zero(ring, zl - z1, lane);
+    // ---- scatter
+    smem_to_global(dst + b, stage, (uint32_t)(a & 15), n, lane);
+  }
+};
+
 __global__ void __launch_bounds__(kThreads, 2)
 k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult* __restrict__ results) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
   __shared__ WorkItem q[kQI];
   __shared__ PipeCtl ctl;
+  __shared__ uint64_t bars[kMovers * kDepth];
   __shared__ ScoutState SS;
   __shared__ uint32_t s_status;
   const RecvOpDev op = ops[blockIdx.x];
@@ -757,6 +975,8 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid < kQI) q[tid].ready = 0;
+  movers_init(bars, tid);
+  uint32_t phase_bits = 0;
   if (tid == 0) {
     s_status = P->status;
     SS.head = P->head;
@@ -787,27 +1007,11 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
       ctl.op_done = 0;
     }
     __syncthreads();
-    if (warp == 0) recv_produce_segment(op, ring, cap, SS, q, &ctl, lane);
-    uint64_t a, b, c;
-    uint32_t n;
-    auto clear_item = [&](uint64_t ia, uint64_t ic, uint32_t in) {  // clear-on-read: exactly what the item retired
-      const uint32_t zhead = (uint32_t)(ic & 0xffff), ztail = (uint32_t)(ic >> 16);
-      const uint64_t zs = (ia + cap - zhead) & mask;
-      const uint64_t zl = (uint64_t)zhead + in + ztail;
-      uint64_t z1 = cap - zs;
-      if (z1 > zl) z1 = zl;
-      coop_zero(ring + zs, z1, lane);
-      if (zl > z1) coop_zero(ring, zl - z1, lane);
-    };
-    while (claim_item(q, &ctl, lane, a, b, c, n)) {
-      // ---- scatter
-      uint8_t* dst = op.dst + b;
-      uint64_t seg1 = cap - a;
-      if (seg1 > n) seg1 = n;
-      coop_copy<true>(dst, ring + a, seg1, lane);
-      if (n > seg1) coop_copy<true>(dst + seg1, ring, n - seg1, lane);
-      __syncwarp();  // every lane's loads are done before any lane clears
-      clear_item(a, c, n);
+    if (warp == 0) {
+      recv_produce_segment(op, ring, cap, SS, q, &ctl, lane);
+    } else {
+      const RecvMove mv{ring, op.dst, cap, mask};
+      mover_run(mv, q, &ctl, stage_mem + (warp - 1) * (kDepth * kStageBytes), &bars[(warp - 1) * kDepth], phase_bits, lane);
     }
     const bool credit = ld_shared_volatile(&SS.credit_flag) != 0;  // stable: the producer finished this segment
     if (credit) __threadfence_system();       // the sender may reuse the space only once it reads as zero
@@ -831,8 +1035,8 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
     results[blockIdx.x].calls = SS.ncalls;
     uint32_t hm;
     uint64_t rd;
-    rx_probe(ring, cap, SS.head, SS.remain, hm, rd);
-    publish_mirror(P->mirror, P, hm, rd);
+    rx_probe<false>(ring, cap, SS.head, SS.remain, hm, rd);
+    publish_mirror_rx(P->mirror, P, hm, rd);
   }
 }
 
@@ -863,7 +1067,8 @@ k_poll_scan(PairDev* __restrict__ pairs, const int32_t* __restrict__ slots, uint
         if (hm) ev |= kEvReadable;
         if (pw) ev |= kEvWritable;
       }
-      publish_mirror(P->mirror, P, hm, rd);
+      publish_mirror_rx(P->mirror, P, hm, rd);
+      publish_mirror_tx(P->mirror, P);
     } else if (st == kStError || st == kStHalfClosed) {
       ev = kEvReadable;
     }
@@ -880,64 +1085,86 @@ k_poll_scan(PairDev* __restrict__ pairs, const int32_t* __restrict__ slots, uint
 }
 
 // =========================================================================
-// k_probe_copy: calibration kernel.  Same decomposition as k_send (one CTA per
-// connection, 4 KiB warp items, same copy primitives) but no framing logic: what
-// this grid shape can reach on this GPU, for src/dst misalignments `mis`.
+// k_probe_copy: calibration kernel.  Same decomposition as k_send / k_recv (one CTA per
+// connection, a producer warp publishing 4 KiB items, the same movers and stages) but no
+// framing logic: what this grid shape can reach on this GPU, for a source misaligned by `mis`.
 // =========================================================================
-__global__ void __launch_bounds__(512, 2)
-k_probe_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t bytes_per_cta, uint64_t stride,
-             uint32_t mis, uint32_t item_bytes, uint32_t dynamic) {
-  __shared__ uint32_t s_next;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+__global__ void __launch_bounds__(kThreads, 2)
+k_probe_copy(uint8_t* __restrict__ dst, uint8_t* __restrict__ src, uint64_t bytes_per_cta, uint64_t stride,
+             uint32_t mis, uint32_t item_bytes, uint32_t mode) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
+  __shared__ WorkItem q[kQI];
+  __shared__ PipeCtl ctl;
+  __shared__ uint64_t bars[kMovers * kDepth];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t* d = dst + (uint64_t)blockIdx.x * stride;
-  const uint8_t* sp = src + (uint64_t)blockIdx.x * stride + mis;
-  const uint64_t nitems = bytes_per_cta / item_bytes;
-  if (threadIdx.x == 0) s_next = 0;
-  __syncthreads();
-  const bool zero_after = (dynamic & 2) != 0;  // recv-like traffic: read src, write dst, clear src
-  uint8_t* sw = const_cast<uint8_t*>(sp);
-  if (dynamic & 1) {
-    while (true) {
-      uint32_t w = 0;
-      if (lane == 0) w = atomicAdd(&s_next, 1u);
-      w = __shfl_sync(0xffffffffu, w, 0);
-      if (w >= nitems) break;
-      if (zero_after) {
-        coop_copy<true>(d + (uint64_t)w * item_bytes, sp + (uint64_t)w * item_bytes, item_bytes, lane);
-        __syncwarp();
-        coop_zero(sw + (uint64_t)w * item_bytes, item_bytes, lane);
-      } else {
-        coop_copy<false>(d + (uint64_t)w * item_bytes, sp + (uint64_t)w * item_bytes, item_bytes, lane);
-      }
-    }
-  } else {
-    for (uint64_t w = warp; w < nitems; w += nwarps) {
-      if (zero_after) {
-        coop_copy<true>(d + w * item_bytes, sp + w * item_bytes, item_bytes, lane);
-        __syncwarp();
-        coop_zero(sw + w * item_bytes, item_bytes, lane);
-      } else {
-        coop_copy<false>(d + w * item_bytes, sp + w * item_bytes, item_bytes, lane);
-      }
-    }
+  uint8_t* sbase = src + (uint64_t)blockIdx.x * stride;  // 16-byte aligned like a ring
+  uint8_t* sp = sbase + mis;
+  if (item_bytes > kChunk) item_bytes = kChunk;
+  const uint32_t nitems = (uint32_t)(bytes_per_cta / item_bytes);
+  if (tid < kQI) q[tid].ready = 0;
+  movers_init(bars, tid);
+  uint32_t phase_bits = 0;
+  if (tid == 0) {
+    ctl.next = 0;
+    ctl.total_items = 0;
+    ctl.seg_done = 0;
+    ctl.op_done = 0;
   }
+  __syncthreads();
+  const bool zero_after = (mode & 2) != 0;  // recv-like traffic: read src, write dst, clear src
+  constexpr uint64_t kBig = 1ull << 62;
+  if (warp == 0) {
+    for (uint32_t it = lane; it < nitems; it += 32) {
+      const uint64_t off = (uint64_t)it * item_bytes;
+      publish_item(q, it, zero_after ? off + mis : reinterpret_cast<uint64_t>(sp + off), off, 0, item_bytes);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      ctl.total_items = nitems;
+      __threadfence_block();
+      *(volatile uint32_t*)&ctl.seg_done = 1;
+    }
+  } else if (zero_after) {
+    const RecvMove mv{sbase, d, kBig, kBig - 1};
+    mover_run(mv, q, &ctl, stage_mem + (warp - 1) * (kDepth * kStageBytes), &bars[(warp - 1) * kDepth], phase_bits, lane);
+  } else {
+    const SendMove mv{d, kBig, kBig - 1};
+    mover_run(mv, q, &ctl, stage_mem + (warp - 1) * (kDepth * kStageBytes), &bars[(warp - 1) * kDepth], phase_bits, lane);
+  }
+}
+
+static void ensure_kernel_attrs() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncSetAttribute(k_send, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
+  cudaFuncSetAttribute(k_recv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
+  cudaFuncSetAttribute(k_probe_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
+  cudaFuncSetAttribute(k_send, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_recv, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_probe_copy, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 
 void launch_probe_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,
                        int threads, uint32_t mis, uint32_t item_bytes, uint32_t dynamic, void* stream) {
-  k_probe_copy<<<nctas, threads, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, bytes_per_cta, stride, mis,
-                                                                         item_bytes, dynamic);
+  (void)threads;
+  ensure_kernel_attrs();
+  k_probe_copy<<<nctas, kThreads, kStageTotal, static_cast<cudaStream_t>(stream)>>>(
+      dst, const_cast<uint8_t*>(src), bytes_per_cta, stride, mis, item_bytes, dynamic);
 }
 
 // ---------------------------------------------------------------- launchers
 
 void launch_send(PairDev* pairs, const SendOpDev* ops, OpResult* results, int nops, void* stream) {
   if (nops <= 0) return;
-  k_send<<<nops, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
+  ensure_kernel_attrs();
+  k_send<<<nops, kThreads, kStageTotal, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
 }
 void launch_recv(PairDev* pairs, const RecvOpDev* ops, OpResult* results, int nops, void* stream) {
   if (nops <= 0) return;
-  k_recv<<<nops, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
+  ensure_kernel_attrs();
+  k_recv<<<nops, kThreads, kStageTotal, static_cast<cudaStream_t>(stream)>>>(pairs, ops, results);
 }
 void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, uint32_t* ready_count,
                       int32_t* ready_slots, int n, void* stream) {
