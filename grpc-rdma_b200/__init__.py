@@ -97,6 +97,10 @@ _SIGS = {
     "b200_poller_remove": (None, [C.c_void_p]),
     "b200_poller_shutdown": (None, []),
     "b200_poller_scan": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.c_uint32)]),
+    "b200_service_start": (C.c_int, [C.c_int]),
+    "b200_service_stop": (None, []),
+    "b200_service_running": (C.c_int, []),
+    "b200_service_stats": (None, [C.POINTER(C.c_uint64)]),
     "b200_pairs_send": (C.c_int, [C.POINTER(SendOp), C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]),
     "b200_pairs_recv": (C.c_int, [C.POINTER(RecvOp), C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]),
     "b200_batch_prepare_send": (C.c_void_p, [C.POINTER(SendOp), C.c_size_t, C.c_int]),

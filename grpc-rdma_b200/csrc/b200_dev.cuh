@@ -117,11 +117,49 @@ constexpr uint32_t kStConnected = 2;
 constexpr uint32_t kStHalfClosed = 3;
 constexpr uint32_t kStError = 5;
 
+// ---- persistent service kernel (k_service): host -> device commands in pinned mapped memory.
+// One command slot per worker CTA; the host writes the fields, then bumps `seq` (release); the
+// CTA polls `seq` (acquire, system scope), runs the op with the same code as k_send / k_recv and
+// answers in SvcDone.  The last CTA of the grid is the poller: it scans the connection table
+// continuously, keeps the host-visible mirrors current and appends readiness CHANGES to the
+// ready ring (warp-aggregated: one atomic per warp).
+constexpr uint32_t kSvcSend = 1, kSvcRecv = 2, kSvcStop = 3;
+struct __align__(64) SvcCmd {
+  uint32_t seq;      // command number, written last by the host
+  uint32_t op;       // kSvcSend / kSvcRecv / kSvcStop
+  int32_t slot;
+  uint32_t flags;    // B200_BATCH_*
+  uint64_t ptr;      // send: SliceDev* (GPU-addressable)   recv: destination
+  uint64_t n;        // send: nslices                        recv: capacity
+  uint64_t byte_idx;
+  uint64_t _pad[3];
+};
+struct __align__(32) SvcDone {
+  uint64_t bytes, calls;
+  uint32_t seq;      // = SvcCmd.seq once the op is finished and its bytes are visible
+  uint32_t _pad[3];
+};
+constexpr uint32_t kReadyRing = 4096;  // entries; entry i of the stream sits at i % kReadyRing
+struct ReadyEntry {                    // one 8-byte store
+  uint32_t stamp;                      // stream index + 1 (0 = never written)
+  uint16_t slot;
+  uint16_t events;                     // kEv* bits now set for the pair (0 = went idle)
+};
+struct SvcPollState {                  // device memory
+  uint32_t hi_slot;                    // scan slots [0, hi_slot)
+  uint32_t stop;
+  uint32_t ready_next;                 // next stream index of the ready ring
+  uint32_t scans;                      // completed scans (liveness)
+};
+
 // launch wrappers (b200_kernels.cu)
 void launch_send(PairDev* pairs, const SendOpDev* ops, OpResult* results, int nops, void* stream);
 void launch_recv(PairDev* pairs, const RecvOpDev* ops, OpResult* results, int nops, void* stream);
 void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, uint32_t* ready_count,
                       int32_t* ready_slots, int n, void* stream);
+
+void launch_service(PairDev* pairs, SvcCmd* cmds, SvcDone* done, SvcPollState* ps, uint32_t* last_ev,
+                    ReadyEntry* ready, uint32_t* host_scans, int nworkers, void* stream);
 
 void launch_probe_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,
                        int threads, uint32_t mis, uint32_t item_bytes, uint32_t dynamic, void* stream);

@@ -538,25 +538,30 @@ struct SendMove {
   }
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
-k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult* __restrict__ results) {
-  extern __shared__ __align__(128) uint8_t stage_mem[];
-  __shared__ WorkItem q[kQI];
-  __shared__ PipeCtl ctl;
-  __shared__ uint64_t bars[kMovers * kDepth];
+// Shared by every kernel of this file: the ticket ring, the stage barriers and the stages.
+struct PipeSmem {
+  WorkItem q[kQI];
+  PipeCtl ctl;
+  uint64_t bars[kMovers * kDepth];
+};
+
+// One Send op (PairPollable::Send, or the rdma_flush loop around it) by the whole CTA.
+// `phase_bits` carries the stage barriers' parities of this thread's warp from op to op.
+__device__ __forceinline__ void send_body(PairDev* __restrict__ pairs, const SendOpDev& op, OpResult* result,
+                                          PipeSmem& pipe, uint8_t* stage_mem, uint32_t& phase_bits) {
+  WorkItem* q = pipe.q;
+  PipeCtl& ctl = pipe.ctl;
+  uint64_t* bars = pipe.bars;
   __shared__ SendPlanState PS;
   __shared__ SendCallScratch CS;
   __shared__ uint32_t foot8[kFootCap];
   __shared__ uint32_t s_nfoot;
   __shared__ unsigned long long s_total;
   __shared__ uint32_t s_status;
-  const SendOpDev op = ops[blockIdx.x];
   PairDev* P = &pairs[op.slot];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid < kQI) q[tid].ready = 0;
-  movers_init(bars, tid);
-  uint32_t phase_bits = 0;
   if (tid == 0) {
     s_total = 0;
     s_status = P->status;
@@ -581,8 +586,8 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
   __syncthreads();
   if (s_status != kStConnected) {  // pair.cc:657
     if (tid == 0) {
-      results[blockIdx.x].bytes = 0;
-      results[blockIdx.x].calls = 0;
+      result->bytes = 0;
+      result->calls = 0;
     }
     return;
   }
@@ -621,8 +626,8 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
   if (tid == 0) {
     P->remote_tail = PS.rt;
     P->partial_write = PS.partial;
-    results[blockIdx.x].bytes = PS.written_total;
-    results[blockIdx.x].calls = PS.ncalls;
+    result->bytes = PS.written_total;
+    result->calls = PS.ncalls;
     publish_mirror_tx(P->mirror, P);
     // loopback wire: the peer lives in this table, refresh its readiness hint
     if (P->peer_slot >= 0 && PS.written_total) {
@@ -637,6 +642,16 @@ k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult*
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_send(PairDev* __restrict__ pairs, const SendOpDev* __restrict__ ops, OpResult* __restrict__ results) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
+  __shared__ PipeSmem pipe;
+  movers_init(pipe.bars, threadIdx.x);
+  uint32_t phase_bits = 0;
+  const SendOpDev op = ops[blockIdx.x];
+  send_body(pairs, op, &results[blockIdx.x], pipe, stage_mem, phase_bits);
 }
 
 // =========================================================================
@@ -962,21 +977,18 @@ struct RecvMove {
   }
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
-k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult* __restrict__ results) {
-  extern __shared__ __align__(128) uint8_t stage_mem[];
-  __shared__ WorkItem q[kQI];
-  __shared__ PipeCtl ctl;
-  __shared__ uint64_t bars[kMovers * kDepth];
+// One Recv op (PairPollable::Recv, or rdma_do_read's loop around it) by the whole CTA.
+__device__ __forceinline__ void recv_body(PairDev* __restrict__ pairs, const RecvOpDev& op, OpResult* result,
+                                          PipeSmem& pipe, uint8_t* stage_mem, uint32_t& phase_bits) {
+  WorkItem* q = pipe.q;
+  PipeCtl& ctl = pipe.ctl;
+  uint64_t* bars = pipe.bars;
   __shared__ ScoutState SS;
   __shared__ uint32_t s_status;
-  const RecvOpDev op = ops[blockIdx.x];
   PairDev* P = &pairs[op.slot];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid < kQI) q[tid].ready = 0;
-  movers_init(bars, tid);
-  uint32_t phase_bits = 0;
   if (tid == 0) {
     s_status = P->status;
     SS.head = P->head;
@@ -991,8 +1003,8 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
   __syncthreads();
   if (s_status != kStConnected) {  // pair.cc:266-268
     if (tid == 0) {
-      results[blockIdx.x].bytes = 0;
-      results[blockIdx.x].calls = 0;
+      result->bytes = 0;
+      result->calls = 0;
     }
     return;
   }
@@ -1031,13 +1043,23 @@ k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult*
     P->moving_head = SS.mh;
     P->remain = SS.remain;
     P->acc = SS.acc;
-    results[blockIdx.x].bytes = SS.delivered;
-    results[blockIdx.x].calls = SS.ncalls;
+    result->bytes = SS.delivered;
+    result->calls = SS.ncalls;
     uint32_t hm;
     uint64_t rd;
     rx_probe<false>(ring, cap, SS.head, SS.remain, hm, rd);
     publish_mirror_rx(P->mirror, P, hm, rd);
   }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_recv(PairDev* __restrict__ pairs, const RecvOpDev* __restrict__ ops, OpResult* __restrict__ results) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
+  __shared__ PipeSmem pipe;
+  movers_init(pipe.bars, threadIdx.x);
+  uint32_t phase_bits = 0;
+  const RecvOpDev op = ops[blockIdx.x];
+  recv_body(pairs, op, &results[blockIdx.x], pipe, stage_mem, phase_bits);
 }
 
 // =========================================================================
@@ -1085,6 +1107,153 @@ k_poll_scan(PairDev* __restrict__ pairs, const int32_t* __restrict__ slots, uint
 }
 
 // =========================================================================
+// k_service: persistent kernel.  Worker CTAs execute Send / Recv commands posted by the host into
+// pinned mapped memory with exactly the code of k_send / k_recv (no launch, no stream sync on the
+// unary path); the last CTA is the poller of the BPEV design (Poller::begin_polling,
+// poller.cc:52-106, and the engine's scan, ev_epollex_rdma_bpev_linux.cc:1104-1145) as a
+// resident scan loop.
+// =========================================================================
+__device__ __forceinline__ void service_poll_loop(PairDev* pairs, SvcPollState* ps, uint32_t* last_ev,
+                                                  ReadyEntry* ready, uint32_t* host_scans) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  __shared__ uint32_t s_hi, s_stop;
+  while (true) {
+    if (tid == 0) {
+      s_hi = *(volatile uint32_t*)&ps->hi_slot;
+      s_stop = *(volatile uint32_t*)&ps->stop;
+    }
+    __syncthreads();
+    const uint32_t hi = s_hi;
+    if (s_stop) break;
+    for (uint32_t base = 0; base < hi; base += kThreads) {
+      const uint32_t slot = base + tid;
+      uint32_t ev = 0, changed = 0;
+      if (slot < hi) {
+        PairDev* P = &pairs[slot];
+        const uint32_t st = *(volatile uint32_t*)&P->status;
+        uint32_t hm = 0;
+        uint64_t rd = 0;
+        if (st == kStConnected) {
+          const uint32_t exit_flag = ld_acquire_u32(&P->credit_exit);
+          rx_probe(P->ring, P->cap, *(volatile uint64_t*)&P->head, *(volatile uint64_t*)&P->remain, hm, rd);
+          const uint32_t pw = *(volatile uint32_t*)&P->partial_write;
+          if (exit_flag == 1) {
+            ev = kEvReadable;  // HalfClosed: force a read event (engine :1130-1137)
+          } else {
+            if (hm) ev |= kEvReadable;
+            if (pw) ev |= kEvWritable;
+          }
+          ev |= (uint32_t)(rd != 0) << 8;  // a frame that became complete is a change too
+        } else if (st == kStError || st == kStHalfClosed) {
+          ev = kEvReadable;
+        }
+        changed = ev != last_ev[slot];
+        if (changed) {
+          last_ev[slot] = ev;
+          // On the loopback wire the kernels that land bytes / return credit refresh the peer's
+          // mirror themselves, in order with their own completion; a second writer here could
+          // only overwrite that with an older view.  Any other wire has no such writer.
+          if (st == kStConnected && P->peer_slot < 0) {
+            publish_mirror_rx(P->mirror, P, hm, rd);
+            publish_mirror_tx(P->mirror, P);
+          }
+        }
+      }
+      // warp-aggregated append of the changes to the ready ring (mapped host memory)
+      const unsigned m = __ballot_sync(0xffffffffu, changed != 0);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        uint32_t idx = 0;
+        if ((int)lane == leader) idx = atomicAdd(&ps->ready_next, (uint32_t)__popc(m));
+        idx = __shfl_sync(0xffffffffu, idx, leader) + __popc(m & ((1u << lane) - 1));
+        if (changed) {
+          __threadfence_system();  // the mirror fields first
+          ReadyEntry e;
+          e.stamp = idx + 1;
+          e.slot = (uint16_t)slot;
+          e.events = (uint16_t)(ev & 0xff);
+          *reinterpret_cast<volatile uint64_t*>(&ready[idx % kReadyRing]) = *reinterpret_cast<uint64_t*>(&e);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t n = ++ps->scans;
+      if ((n & 1023u) == 0) *(volatile uint32_t*)host_scans = n;  // liveness beacon
+    }
+    __nanosleep(200);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_service(PairDev* __restrict__ pairs, SvcCmd* cmds, SvcDone* done, SvcPollState* ps, uint32_t* last_ev,
+          ReadyEntry* ready, uint32_t* host_scans, int nworkers) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
+  __shared__ PipeSmem pipe;
+  __shared__ SvcCmd s_cmd;
+  __shared__ OpResult s_res;
+  if ((int)blockIdx.x == nworkers) {
+    service_poll_loop(pairs, ps, last_ev, ready, host_scans);
+    return;
+  }
+  const uint32_t tid = threadIdx.x;
+  movers_init(pipe.bars, tid);
+  uint32_t phase_bits = 0;
+  SvcCmd* cmd = &cmds[blockIdx.x];
+  SvcDone* dn = &done[blockIdx.x];
+  uint32_t expect = 1;
+  while (true) {
+    if (tid == 0) {
+      uint32_t backoff = 0;
+      while (ld_acquire_u32(&cmd->seq) != expect)  // one PCIe read per poll
+        if (++backoff > 64) __nanosleep(100);
+      s_cmd.op = *(volatile uint32_t*)&cmd->op;
+      s_cmd.slot = *(volatile int32_t*)&cmd->slot;
+      s_cmd.flags = *(volatile uint32_t*)&cmd->flags;
+      s_cmd.ptr = *(volatile uint64_t*)&cmd->ptr;
+      s_cmd.n = *(volatile uint64_t*)&cmd->n;
+      s_cmd.byte_idx = *(volatile uint64_t*)&cmd->byte_idx;
+      s_res.bytes = 0;
+      s_res.calls = 0;
+    }
+    __syncthreads();
+    const uint32_t opc = s_cmd.op;
+    if (opc == kSvcStop) break;
+    if (opc == kSvcSend) {
+      SendOpDev op;
+      op.slot = s_cmd.slot;
+      op.flags = s_cmd.flags;
+      op.slices = reinterpret_cast<const SliceDev*>(s_cmd.ptr);
+      op.nslices = s_cmd.n;
+      op.byte_idx = s_cmd.byte_idx;
+      send_body(pairs, op, &s_res, pipe, stage_mem, phase_bits);
+    } else if (opc == kSvcRecv) {
+      RecvOpDev op;
+      op.slot = s_cmd.slot;
+      op.flags = s_cmd.flags;
+      op.dst = reinterpret_cast<uint8_t*>(s_cmd.ptr);
+      op.cap = s_cmd.n;
+      recv_body(pairs, op, &s_res, pipe, stage_mem, phase_bits);
+    }
+    __threadfence_system();  // every thread's bytes (ring, host destination, mirrors) before the answer
+    __syncthreads();
+    if (tid == 0) {
+      volatile SvcDone* vd = dn;
+      vd->bytes = s_res.bytes;
+      vd->calls = s_res.calls;
+      __threadfence_system();
+      vd->seq = expect;
+    }
+    expect++;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence_system();
+    *(volatile uint32_t*)&dn->seq = expect;  // stop acknowledged
+  }
+}
+
+// =========================================================================
 // k_probe_copy: calibration kernel.  Same decomposition as k_send / k_recv (one CTA per
 // connection, a producer warp publishing 4 KiB items, the same movers and stages) but no
 // framing logic: what this grid shape can reach on this GPU, for a source misaligned by `mis`.
@@ -1093,9 +1262,10 @@ __global__ void __launch_bounds__(kThreads, 2)
 k_probe_copy(uint8_t* __restrict__ dst, uint8_t* __restrict__ src, uint64_t bytes_per_cta, uint64_t stride,
              uint32_t mis, uint32_t item_bytes, uint32_t mode) {
   extern __shared__ __align__(128) uint8_t stage_mem[];
-  __shared__ WorkItem q[kQI];
-  __shared__ PipeCtl ctl;
-  __shared__ uint64_t bars[kMovers * kDepth];
+  __shared__ PipeSmem pipe;
+  WorkItem* q = pipe.q;
+  PipeCtl& ctl = pipe.ctl;
+  uint64_t* bars = pipe.bars;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t* d = dst + (uint64_t)blockIdx.x * stride;
   uint8_t* sbase = src + (uint64_t)blockIdx.x * stride;  // 16-byte aligned like a ring
@@ -1144,6 +1314,15 @@ static void ensure_kernel_attrs() {
   cudaFuncSetAttribute(k_send, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(k_recv, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(k_probe_copy, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_service, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
+  cudaFuncSetAttribute(k_service, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+
+void launch_service(PairDev* pairs, SvcCmd* cmds, SvcDone* done, SvcPollState* ps, uint32_t* last_ev,
+                    ReadyEntry* ready, uint32_t* host_scans, int nworkers, void* stream) {
+  ensure_kernel_attrs();
+  k_service<<<nworkers + 1, kThreads, kStageTotal, static_cast<cudaStream_t>(stream)>>>(
+      pairs, cmds, done, ps, last_ev, ready, host_scans, nworkers);
 }
 
 void launch_probe_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,

@@ -23,6 +23,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -164,6 +165,34 @@ struct Runtime {
   uint32_t* h_scan_count = nullptr;
   int32_t* h_scan_ready = nullptr;
   std::mutex scan_mu;
+  // persistent service kernel (b200_service_*)
+  struct SvcWorker {
+    std::mutex mu;
+    uint32_t seq = 0;
+    SliceDev* slices = nullptr;  // pinned, kMaxSgeLimit + 1 entries
+    uint8_t* bounce_tx = nullptr;
+    uint8_t* bounce_rx = nullptr;
+    uint64_t bounce_tx_cap = 0, bounce_rx_cap = 0;
+  };
+  std::atomic<bool> svc_running{false};
+  int svc_workers = 0;
+  cudaStream_t svc_stream = nullptr;
+  SvcCmd* svc_cmds = nullptr;          // pinned, mapped
+  SvcDone* svc_done = nullptr;         // pinned, mapped
+  ReadyEntry* svc_ready = nullptr;     // pinned, mapped
+  uint32_t* svc_host_scans = nullptr;  // pinned, mapped
+  SvcPollState* d_svc_ps = nullptr;
+  uint32_t* d_svc_last_ev = nullptr;
+  SvcWorker* svc_w = nullptr;
+  uint32_t svc_hi_slot = 0;
+  std::atomic<uint64_t> svc_ops{0}, svc_ready_seen{0}, svc_ready_overflows{0};
+  uint32_t svc_ready_head = 0;      // next stream index the host expects (under scan_mu)
+  std::vector<uint16_t> svc_level;  // events pending per slot, as last reported by the device poller
+  std::mutex grave_mu;
+  std::vector<std::pair<void*, int>> graveyard;  // frees deferred while the persistent kernel runs
+  // registry of memory this library handed out (skips cudaPointerGetAttributes on the unary path)
+  std::mutex reg_mu;
+  std::map<uintptr_t, size_t> reg_ranges;
 };
 
 Runtime& R() {
@@ -190,7 +219,9 @@ bool write_setup(Runtime& r, b200_pair* p, const PairDev& hd) {
 }
 
 // what kind of memory is this? 0 = unregistered host, 1 = GPU-addressable
+bool reg_has(const void* p);
 int mem_kind(const void* p) {
+  if (reg_has(p)) return 1;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
@@ -201,6 +232,39 @@ int mem_kind(const void* p) {
 
 void kick(b200_pair* p) {
   if (p->wakeup_fd >= 0) (void)eventfd_write(p->wakeup_fd, 1);
+}
+
+// cudaFree / cudaFreeHost synchronise the whole device, which never completes while the
+// persistent service kernel is resident: such frees wait in a graveyard until it stops.
+void rt_free(void* p, int host) {
+  if (!p) return;
+  Runtime& r = R();
+  if (r.svc_running.load()) {
+    std::lock_guard<std::mutex> lk(r.grave_mu);
+    r.graveyard.push_back({p, host});
+    return;
+  }
+  if (host) cudaFreeHost(p);
+  else cudaFree(p);
+}
+
+void reg_add(const void* p, size_t n) {
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.reg_mu);
+  r.reg_ranges[(uintptr_t)p] = n;
+}
+void reg_del(const void* p) {
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.reg_mu);
+  r.reg_ranges.erase((uintptr_t)p);
+}
+bool reg_has(const void* p) {
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.reg_mu);
+  auto it = r.reg_ranges.upper_bound((uintptr_t)p);
+  if (it == r.reg_ranges.begin()) return false;
+  --it;
+  return (uintptr_t)p < it->first + it->second;
 }
 
 }  // namespace
@@ -271,7 +335,10 @@ extern "C" int b200_init(int device) {
   static bool at_exit_registered = false;
   if (!at_exit_registered) {
     at_exit_registered = true;
-    atexit(b200_poller_shutdown);  // poller threads must be joined before static destruction
+    atexit([] {  // poller threads joined and the persistent kernel gone before static destruction
+      b200_poller_shutdown();
+      b200_service_stop();
+    });
   }
   r.inited = true;
   return 0;
@@ -279,6 +346,7 @@ extern "C" int b200_init(int device) {
 
 extern "C" void b200_shutdown(void) {
   b200_poller_shutdown();
+  b200_service_stop();
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.mu);
   if (!r.inited) return;
@@ -373,26 +441,37 @@ extern "C" void* b200_mem_alloc_device(size_t bytes) {
   void* p = nullptr;
   cudaSetDevice(R().dev);
   if (!CU_OK(cudaMalloc(&p, bytes ? bytes : 1))) return nullptr;
+  reg_add(p, bytes ? bytes : 1);
   return p;
 }
 extern "C" void b200_mem_free_device(void* p) {
-  if (p) cudaFree(p);
+  if (!p) return;
+  reg_del(p);
+  rt_free(p, 0);
 }
 extern "C" void* b200_mem_alloc_host(size_t bytes) {
   if (!ensure_init()) return nullptr;
   void* p = nullptr;
   cudaSetDevice(R().dev);
   if (!CU_OK(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable))) return nullptr;
+  reg_add(p, bytes ? bytes : 1);
   return p;
 }
 extern "C" void b200_mem_free_host(void* p) {
-  if (p) cudaFreeHost(p);
+  if (!p) return;
+  reg_del(p);
+  rt_free(p, 1);
 }
 extern "C" int b200_mem_register_host(void* p, size_t bytes) {
   if (!ensure_init()) return -1;
-  return CU_OK(cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable)) ? 0 : -1;
+  if (!CU_OK(cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable))) return -1;
+  reg_add(p, bytes);
+  return 0;
 }
-extern "C" int b200_mem_unregister_host(void* p) { return CU_OK(cudaHostUnregister(p)) ? 0 : -1; }
+extern "C" int b200_mem_unregister_host(void* p) {
+  reg_del(p);
+  return CU_OK(cudaHostUnregister(p)) ? 0 : -1;
+}
 extern "C" int b200_memcpy(void* dst, const void* src, size_t bytes, int dir, void* stream) {
   if (!ensure_init()) return -1;
   cudaMemcpyKind k = dir == 0 ? cudaMemcpyHostToDevice : dir == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
@@ -463,7 +542,7 @@ extern "C" void b200_pair_init(b200_pair* p) {
     return;
   }
   if (p->ring && p->cap != cap) {
-    cudaFree(p->ring);
+    rt_free(p->ring, 0);
     p->ring = nullptr;
   }
   if (!p->ring) {
@@ -490,6 +569,11 @@ extern "C" void b200_pair_init(b200_pair* p) {
     p->error = t_err;
     p->status = B200_ERROR;
     return;
+  }
+  if (r.svc_running.load() && (uint32_t)p->slot + 1 > r.svc_hi_slot) {
+    r.svc_hi_slot = (uint32_t)p->slot + 1;
+    cudaMemcpyAsync(&r.d_svc_ps->hi_slot, &r.svc_hi_slot, 4, cudaMemcpyHostToDevice, r.stream);
+    cudaStreamSynchronize(r.stream);
   }
   // drop a stale registration, then publish the new address
   if (p->self.qpn) r.by_qpn.erase(p->self.qpn);
@@ -657,11 +741,215 @@ extern "C" int b200_pair_copy_ring(b200_pair* p, void* host_dst, uint64_t cap) {
   return CU_OK(cudaMemcpy(host_dst, p->ring, p->cap, cudaMemcpyDeviceToHost)) ? 0 : -1;
 }
 
+// ================================================================== service
+//
+// The persistent kernel of the unary path: worker CTAs take Send / Recv commands from pinned
+// mapped memory (no launch, no stream synchronisation per call) and a poller CTA keeps the
+// mirrors and the ready ring current (no scan launches).  While it runs, b200_pair_send / recv
+// are routed through it; the batch entry points keep launching their own kernels beside it.
+
+static bool ensure_bounce(uint8_t** buf, uint64_t* cap, uint64_t need);
+
+extern "C" int b200_service_start(int workers) {
+  if (!ensure_init()) return -1;
+  Runtime& r = R();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (r.svc_running.load()) return 0;
+  if (workers <= 0) workers = (int)env_long("B200_SERVICE_WORKERS", 16);
+  if (workers > 128) workers = 128;
+  cudaSetDevice(r.dev);
+  auto halloc = [&](void** p, size_t n) {
+    if (!CU_OK(cudaHostAlloc(p, n, cudaHostAllocMapped | cudaHostAllocPortable))) return false;
+    memset(*p, 0, n);
+    return true;
+  };
+  if (!r.svc_stream && !CU_OK(cudaStreamCreateWithFlags(&r.svc_stream, cudaStreamNonBlocking))) return -1;
+  if (!halloc((void**)&r.svc_cmds, sizeof(SvcCmd) * workers) || !halloc((void**)&r.svc_done, sizeof(SvcDone) * workers) ||
+      !halloc((void**)&r.svc_ready, sizeof(ReadyEntry) * kReadyRing) || !halloc((void**)&r.svc_host_scans, 64))
+    return -1;
+  if (!CU_OK(cudaMalloc(&r.d_svc_ps, sizeof(SvcPollState))) || !CU_OK(cudaMalloc(&r.d_svc_last_ev, 4 * kMaxPairs)))
+    return -1;
+  r.svc_hi_slot = 0;
+  for (b200_pair* p : r.all_pairs)
+    if ((uint32_t)p->slot + 1 > r.svc_hi_slot) r.svc_hi_slot = (uint32_t)p->slot + 1;
+  SvcPollState ps{};
+  ps.hi_slot = r.svc_hi_slot;
+  if (!CU_OK(cudaMemcpyAsync(r.d_svc_ps, &ps, sizeof(ps), cudaMemcpyHostToDevice, r.stream)) ||
+      !CU_OK(cudaMemsetAsync(r.d_svc_last_ev, 0, 4 * kMaxPairs, r.stream)) || !CU_OK(cudaStreamSynchronize(r.stream)))
+    return -1;
+  r.svc_w = new Runtime::SvcWorker[workers];
+  for (int w = 0; w < workers; w++)
+    if (!halloc((void**)&r.svc_w[w].slices, sizeof(SliceDev) * (kMaxSgeLimit + 1))) return -1;
+  r.svc_workers = workers;
+  r.svc_ready_head = 0;
+  r.svc_level.assign(kMaxPairs, 0);
+  launch_service(r.d_pairs, r.svc_cmds, r.svc_done, r.d_svc_ps, r.d_svc_last_ev, r.svc_ready, r.svc_host_scans, workers,
+                 r.svc_stream);
+  r.launches++;
+  if (!CU_OK(cudaGetLastError())) return -1;
+  r.svc_running = true;
+  return 0;
+}
+
+extern "C" int b200_service_running(void) { return R().svc_running.load() ? R().svc_workers : 0; }
+
+extern "C" void b200_service_stop(void) {
+  Runtime& r = R();
+  if (!r.inited || !r.svc_running.load()) return;
+  cudaSetDevice(r.dev);
+  for (int w = 0; w < r.svc_workers; w++) {
+    std::lock_guard<std::mutex> lk(r.svc_w[w].mu);
+    SvcCmd* c = &r.svc_cmds[w];
+    c->op = kSvcStop;
+    std::atomic_thread_fence(std::memory_order_release);
+    *(volatile uint32_t*)&c->seq = ++r.svc_w[w].seq;
+  }
+  uint32_t one = 1;
+  cudaMemcpyAsync(&r.d_svc_ps->stop, &one, 4, cudaMemcpyHostToDevice, r.stream);
+  cudaStreamSynchronize(r.stream);
+  cudaStreamSynchronize(r.svc_stream);  // the kernel exits
+  r.svc_running = false;
+  for (int w = 0; w < r.svc_workers; w++) {
+    cudaFreeHost(r.svc_w[w].slices);
+    if (r.svc_w[w].bounce_tx) cudaFreeHost(r.svc_w[w].bounce_tx);
+    if (r.svc_w[w].bounce_rx) cudaFreeHost(r.svc_w[w].bounce_rx);
+  }
+  delete[] r.svc_w;
+  r.svc_w = nullptr;
+  cudaFreeHost(r.svc_cmds);
+  cudaFreeHost(r.svc_done);
+  cudaFreeHost(r.svc_ready);
+  cudaFreeHost(r.svc_host_scans);
+  cudaFree(r.d_svc_ps);
+  cudaFree(r.d_svc_last_ev);
+  r.svc_cmds = nullptr;
+  r.svc_done = nullptr;
+  r.svc_ready = nullptr;
+  r.svc_host_scans = nullptr;
+  r.d_svc_ps = nullptr;
+  r.d_svc_last_ev = nullptr;
+  r.svc_workers = 0;
+  std::vector<std::pair<void*, int>> dead;
+  {
+    std::lock_guard<std::mutex> lk(r.grave_mu);
+    dead.swap(r.graveyard);
+  }
+  for (auto& d : dead) {
+    if (d.second) cudaFreeHost(d.first);
+    else cudaFree(d.first);
+  }
+}
+
+// [0] ops executed, [1] ready-ring entries consumed by the host poller, [2] ready-ring overruns,
+// [3] poller scans reported by the device (updated every 1024 scans)
+extern "C" void b200_service_stats(uint64_t out[4]) {
+  Runtime& r = R();
+  out[0] = r.svc_ops.load();
+  out[1] = r.svc_ready_seen.load();
+  out[2] = r.svc_ready_overflows.load();
+  out[3] = r.svc_host_scans ? *(volatile uint32_t*)r.svc_host_scans : 0;
+}
+
+// post one command to the worker that owns the pair and wait for its answer
+static bool svc_call(Runtime& r, Runtime::SvcWorker& w, int wi, uint32_t op, int slot, uint64_t ptr, uint64_t n,
+                     uint64_t byte_idx, uint64_t* bytes) {
+  SvcCmd* c = &r.svc_cmds[wi];
+  volatile SvcDone* d = &r.svc_done[wi];
+  c->op = op;
+  c->slot = slot;
+  c->flags = B200_BATCH_ONE_CALL;
+  c->ptr = ptr;
+  c->n = n;
+  c->byte_idx = byte_idx;
+  const uint32_t seq = ++w.seq;
+  std::atomic_thread_fence(std::memory_order_release);
+  *(volatile uint32_t*)&c->seq = seq;
+  const auto t0 = std::chrono::steady_clock::now();
+  uint32_t spins = 0;
+  while (d->seq != seq) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xfffff) == 0 &&
+        std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) {
+      set_err("b200 service: command timed out");
+      return false;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  *bytes = d->bytes;
+  r.svc_ops++;
+  return true;
+}
+
+static uint64_t svc_send(Runtime& r, b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
+  const int wi = p->slot % r.svc_workers;
+  Runtime::SvcWorker& w = r.svc_w[wi];
+  std::lock_guard<std::mutex> lk(w.mu);
+  const size_t look = n < (size_t)r.cfg.max_sge ? n : (size_t)r.cfg.max_sge;
+  uint64_t rest = 0;
+  for (size_t i = look; i < n; i++) rest += slices[i].len;
+  uint64_t bounce_off = 0;
+  for (size_t i = 0; i < look; i++) {
+    const uint8_t* ptr = (const uint8_t*)slices[i].ptr;
+    const uint64_t len = slices[i].len;
+    if (len && mem_kind(ptr) == 0) {  // unregistered host memory: stage like the reference's send buffer
+      const uint64_t skip = i == 0 ? byte_idx : 0;
+      const uint64_t useful = len - skip;
+      const uint64_t limit = p->cap / 2;
+      uint64_t take = useful < limit ? useful : limit;
+      if (!ensure_bounce(&w.bounce_tx, &w.bounce_tx_cap, p->cap + 16 * (kMaxSgeLimit + 4))) return 0;
+      if (bounce_off + take > w.bounce_tx_cap) take = w.bounce_tx_cap - bounce_off;
+      memcpy(w.bounce_tx + bounce_off, ptr + skip, take);
+      w.slices[i].ptr = w.bounce_tx + bounce_off - skip;
+      bounce_off += (take + 15) & ~15ull;
+    } else {
+      w.slices[i].ptr = ptr;
+    }
+    w.slices[i].len = len;
+  }
+  size_t nsl = look;
+  if (rest) {
+    w.slices[nsl].ptr = nullptr;
+    w.slices[nsl].len = rest;
+    nsl++;
+  }
+  uint64_t bytes = 0;
+  if (!svc_call(r, w, wi, kSvcSend, p->slot, (uint64_t)(uintptr_t)w.slices, nsl, byte_idx, &bytes)) {
+    p->error = t_err;
+    p->status = B200_ERROR;
+    return 0;
+  }
+  return bytes;
+}
+
+static uint64_t svc_recv(Runtime& r, b200_pair* p, void* dst, uint64_t cap) {
+  const int wi = p->slot % r.svc_workers;
+  Runtime::SvcWorker& w = r.svc_w[wi];
+  std::lock_guard<std::mutex> lk(w.mu);
+  const bool bounce = mem_kind(dst) == 0;
+  uint8_t* kdst = (uint8_t*)dst;
+  uint64_t kcap = cap;
+  if (bounce) {
+    if (kcap > p->cap) kcap = p->cap;
+    if (!ensure_bounce(&w.bounce_rx, &w.bounce_rx_cap, p->cap)) return 0;
+    kdst = w.bounce_rx;
+  }
+  uint64_t bytes = 0;
+  if (!svc_call(r, w, wi, kSvcRecv, p->slot, (uint64_t)(uintptr_t)kdst, kcap, 0, &bytes)) {
+    p->error = t_err;
+    p->status = B200_ERROR;
+    return 0;
+  }
+  if (bounce && bytes) memcpy(dst, w.bounce_rx, bytes);
+  return bytes;
+}
+
 // ================================================================ single call
 
 static bool ensure_bounce(uint8_t** buf, uint64_t* cap, uint64_t need) {
   if (*cap >= need) return true;
-  if (*buf) cudaFreeHost(*buf);
+  if (*buf) rt_free(*buf, 1);
   *buf = nullptr;
   *cap = 0;
   if (!CU_OK(cudaHostAlloc((void**)buf, need, cudaHostAllocMapped | cudaHostAllocPortable))) return false;
@@ -672,6 +960,11 @@ static bool ensure_bounce(uint8_t** buf, uint64_t* cap, uint64_t need) {
 extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
   if (!p || !ensure_init()) return 0;
   Runtime& r = R();
+  if (r.svc_running.load()) {
+    if (p->status != B200_CONNECTED || n == 0) return 0;
+    if (((volatile PairMirror*)p->mirror)->peer_exit == 1) return 0;
+    return svc_send(r, p, slices, n, byte_idx);
+  }
   std::lock_guard<std::mutex> lk(r.mu);
   if (p->status != B200_CONNECTED || n == 0) return 0;
   // The peer told us it left (peer_exit): its ring may already belong to a new
@@ -732,6 +1025,10 @@ extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_
 extern "C" uint64_t b200_pair_recv(b200_pair* p, void* dst, uint64_t cap) {
   if (!p || !ensure_init()) return 0;
   Runtime& r = R();
+  if (r.svc_running.load()) {
+    if (p->status != B200_CONNECTED || cap == 0) return 0;
+    return svc_recv(r, p, dst, cap);
+  }
   std::lock_guard<std::mutex> lk(r.mu);
   if (p->status != B200_CONNECTED || cap == 0) return 0;
   cudaSetDevice(r.dev);
@@ -1031,11 +1328,11 @@ extern "C" int b200_batch_calls(b200_batch* b, uint64_t* out) {
 
 extern "C" void b200_batch_destroy(b200_batch* b) {
   if (!b) return;
-  if (b->d_ops) cudaFree(b->d_ops);
-  if (b->d_slices) cudaFree(b->d_slices);
-  if (b->d_results) cudaFree(b->d_results);
-  if (b->d_stage) cudaFree(b->d_stage);
-  if (b->h_results) cudaFreeHost(b->h_results);
+  rt_free(b->d_ops, 0);
+  rt_free(b->d_slices, 0);
+  rt_free(b->d_results, 0);
+  rt_free(b->d_stage, 0);
+  rt_free(b->h_results, 1);
   delete b;
 }
 
@@ -1089,10 +1386,48 @@ extern "C" int b200_poller_scan(b200_pair* const* pairs, size_t n, uint32_t* eve
   return (int)r.h_scan_count[0];
 }
 
+// Service mode: the device poller reports readiness CHANGES through the ready ring; the host keeps
+// the level per pair and kicks the eventfd of every registered pair that has events pending and
+// whose eventfd is not signalled already (poller.cc:73-101) -- no kernel launch on this path.
+static void poller_service_pass(Runtime& r, const std::vector<b200_pair*>& snap) {
+  std::unique_lock<std::mutex> lk(r.scan_mu, std::try_to_lock);
+  if (!lk.owns_lock()) return;
+  if (r.svc_level.size() != (size_t)kMaxPairs) r.svc_level.assign(kMaxPairs, 0);
+  uint64_t n = 0;
+  while (r.svc_ready) {
+    const uint64_t raw = *reinterpret_cast<volatile uint64_t*>(&r.svc_ready[r.svc_ready_head % kReadyRing]);
+    ReadyEntry e;
+    memcpy(&e, &raw, 8);
+    if (e.stamp == r.svc_ready_head + 1) {
+      r.svc_level[e.slot] = e.events;
+      r.svc_ready_head++;
+      n++;
+    } else if ((int32_t)(e.stamp - (r.svc_ready_head + 1)) > 0) {
+      // the device lapped the ring: rebuild the levels from the mirrors and resume at this entry
+      r.svc_ready_overflows++;
+      for (b200_pair* p : snap) {
+        volatile PairMirror* m = p->mirror;
+        r.svc_level[p->slot] = (uint16_t)((m->has_message || m->peer_exit ? kEvReadable : 0) |
+                                           (m->partial_write ? kEvWritable : 0));
+      }
+      r.svc_ready_head = e.stamp - 1;
+    } else {
+      break;
+    }
+  }
+  if (n) r.svc_ready_seen += n;
+  for (b200_pair* p : snap) {
+    if (!r.svc_level[p->slot]) continue;
+    struct pollfd pfd = {p->wakeup_fd, POLLIN, 0};
+    if (poll(&pfd, 1, 0) <= 0) kick(p);
+  }
+}
+
 static void poller_main(int /*id*/) {
   Runtime& r = R();
   std::vector<b200_pair*> snap;
   std::vector<uint32_t> ev;
+  uint32_t idle = 0;
   while (r.poll_running.load()) {
     {
       std::unique_lock<std::mutex> lk(r.pmu);
@@ -1102,6 +1437,11 @@ static void poller_main(int /*id*/) {
         continue;
       }
       snap = r.pollables;
+    }
+    if (r.svc_running.load()) {
+      poller_service_pass(r, snap);
+      if ((++idle & 63) == 0) std::this_thread::yield();
+      continue;
     }
     ev.assign(snap.size(), 0);
     int nready = b200_poller_scan(snap.data(), snap.size(), ev.data());

@@ -174,6 +174,29 @@ void b200_poller_shutdown(void);
 #define B200_EV_WRITABLE 0x4u /* EPOLLOUT: HasPendingWrites */
 int b200_poller_scan(b200_pair* const* pairs, size_t n, uint32_t* events);
 
+/* ----------------------------------------------------------------- service */
+/*
+ * The persistent kernel of the unary path (the "persistent warp-per-connection kernel" and the
+ * busy-poll half of the BPEV completion loop).  b200_service_start(workers) launches ONE resident
+ * kernel: `workers` CTAs that execute Send / Recv commands the host posts into pinned mapped
+ * memory -- the same device code as the one-shot kernels, but no launch and no stream
+ * synchronisation per call -- plus one poller CTA that scans the connection table continuously,
+ * keeps every pair's host-visible mirror current (so HasMessage / HasPendingWrites / get_status
+ * stay wait-free host reads without any scan launch) and appends readiness CHANGES to a ready
+ * ring in mapped host memory with one atomic per warp.  While it runs, b200_pair_send / recv go
+ * through it and the background Poller threads consume the ready ring instead of launching
+ * scans.  workers <= 0: B200_SERVICE_WORKERS (16).  Returns 0 / -1.
+ * Device-wide synchronisation (cudaDeviceSynchronize, cudaFree) never completes while a
+ * persistent kernel is resident: the library defers its own frees until b200_service_stop, and
+ * callers must use stream-level waits.
+ */
+int b200_service_start(int workers);
+void b200_service_stop(void);
+int b200_service_running(void); /* number of worker CTAs, 0 = not running */
+/* out[0] commands executed, [1] ready-ring entries consumed, [2] ready-ring overruns,
+ * [3] device poller scans (updated every 1024 scans) */
+void b200_service_stats(uint64_t out[4]);
+
 /* ------------------------------------------------------------------- batch */
 /*
  * B200-native widening of Send/Recv: one kernel launch serves many pairs
