@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-unary", action="store_true")
+    ap.add_argument("--unary-bytes", type=int, default=1024)
+    ap.add_argument("--unary-iters", type=int, default=2000)
+    ap.add_argument("--service-workers", type=int, default=16)
     ap.add_argument("--stagger", type=int, default=0, help="1 = de-correlate the connections' ring positions first")
     return ap.parse_args()
 
@@ -333,6 +337,15 @@ def main():
         e2e = run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist if world > 1 else None, dev, stream, sh,
                       build_batches)
 
+    unary = None
+    if rank == 0 and not args.no_unary:
+        for b in (bs, br):
+            b.destroy()
+        try:
+            unary = run_unary(args, pkg, L, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as exc:  # never take the streaming line down
+            unary = {"error": repr(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -365,6 +378,7 @@ def main():
                          "step_frac": (conns * (tx_alg + rx_alg) / (t_dev_ms / K * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "unary": unary,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
@@ -373,6 +387,61 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _pct(rtt_ns):
+    import numpy as np
+    r = np.sort(np.asarray(rtt_ns).reshape(-1)) / 1e3
+    return {"p50_us": float(r[len(r) // 2]), "p99_us": float(r[int(len(r) * 0.99)]), "mean_us": float(r.mean())}
+
+
+def run_unary(args, pkg, L, with_cpu):
+    """BASELINE config 3 at the pair level: M-byte request + M-byte echo (default 1 KiB), round-trip time per
+    call, 1 and 256 connections.  B200: through the C ABI with registered HOST buffers and the persistent
+    service kernel (no launch per call; every request and echo crosses PCIe both ways).  Beside it the
+    reference's own PairPollable ping-pong on the host cores (memcpy wire: no NIC, no PCIe in its path)."""
+    import numpy as np
+    PP = C.CDLL(os.path.join(os.path.dirname(pkg.LIB_PATH), "libb200_pingpong.so"))
+    PP.b200_pp_run.restype = C.c_double
+    PP.b200_pp_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint64)]
+    m, iters = args.unary_bytes, args.unary_iters
+    pkg.config_set("GRPC_RDMA_RING_BUFFER_SIZE_KB", 4096)   # the reference's default ring (config.cc:90-96)
+    out = {"msg_bytes": m, "ring_kb": 4096, "b200": {}, "cpu_reference": None,
+           "path": "b200_pair_send / has_message / recv on registered host buffers, persistent service kernel "
+                   "(%d worker CTAs + 1 poller CTA)" % args.service_workers}
+    launches0 = L.b200_launch_count()
+    if L.b200_service_start(args.service_workers) != 0:
+        return {"error": "b200_service_start: " + pkg.last_error()}
+    try:
+        for conns, groups in ((1, 1), (256, 8)):
+            it = iters if conns == 1 else max(50, iters // 20)
+            rtt = np.zeros(conns * it, dtype=np.uint64)
+            t = PP.b200_pp_run(conns, groups, it, max(10, it // 10), m, rtt.ctypes.data_as(C.POINTER(C.c_uint64)))
+            if t < 0:
+                out["b200"]["conns_%d" % conns] = {"error": "pingpong driver rc %d" % int(t)}
+                continue
+            d = _pct(rtt)
+            d.update({"round_trips_per_s": conns * it / t, "client_threads": groups, "server_threads": groups,
+                      "iters_per_conn": it})
+            out["b200"]["conns_%d" % conns] = d
+    finally:
+        L.b200_service_stop()
+    out["kernel_launches_during_unary"] = int(L.b200_launch_count() - launches0)   # 1 = the service kernel itself
+    if with_cpu:
+        try:
+            eng, kind = cpu_engine()
+            if hasattr(eng, "bench_pingpong"):
+                ref = {"kind": kind}
+                for conns, groups in ((1, 1), (256, 8)):
+                    it = iters if conns == 1 else max(50, iters // 20)
+                    t, rtt = eng.bench_pingpong(conns, groups, it, max(10, it // 10), m, 4096 * 1024)
+                    d = _pct(rtt)
+                    d.update({"round_trips_per_s": conns * it / t, "threads": 2 * groups})
+                    ref["conns_%d" % conns] = d
+                out["cpu_reference"] = ref
+        except Exception as exc:
+            out["cpu_reference"] = {"error": repr(exc)}
+    return out
 
 
 def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stream, sh, build_batches):

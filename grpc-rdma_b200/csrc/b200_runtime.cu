@@ -19,7 +19,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/eventfd.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -86,6 +88,12 @@ struct b200_pair {
   AddrBlob self{};
   AddrBlob peer{};
   b200_pair* peer_local = nullptr;  // loopback wire
+  // nvlink wire: the peer lives in another process (another GPU of the box); its ring and its
+  // row of the connection table are mapped here through CUDA IPC
+  bool remote = false;
+  uint8_t* remote_ring = nullptr;
+  uint64_t* remote_credit = nullptr;
+  std::string wire_file;  // this pair's descriptor under /dev/shm (unlinked on Disconnect)
   bool in_poller = false;
 };
 
@@ -144,6 +152,9 @@ struct Runtime {
   std::map<uint32_t, b200_pair*> by_qpn;  // loopback wire registry
   uint32_t next_qpn = 0x200;
   uint32_t cookie = 0;
+  bool ipc_wire = false;                 // publish CUDA IPC descriptors (B200_IPC_WIRE / WORLD_SIZE > 1)
+  cudaIpcMemHandle_t pairs_handle{};     // d_pairs, exported once
+  std::map<uint32_t, PairDev*> peer_tables;  // other processes' connection tables, by cookie
   // single-call staging (pinned, GPU-mapped)
   SendOpDev* h_sop = nullptr;
   RecvOpDev* h_rop = nullptr;
@@ -258,6 +269,23 @@ void reg_del(const void* p) {
   std::lock_guard<std::mutex> lk(r.reg_mu);
   r.reg_ranges.erase((uintptr_t)p);
 }
+// nvlink wire bootstrap.  The 48-byte address blob has no room for CUDA IPC handles, so -- like the
+// reference's memory-region exchange after the QP is up (pair.cc:472-486,513-526) -- the handles
+// travel out of band: every pair publishes a descriptor under /dev/shm keyed by (process cookie,
+// qpn), both of which are in the blob.
+struct WireDesc {
+  uint32_t magic, psn;
+  int32_t dev, slot;
+  uint64_t cap;
+  cudaIpcMemHandle_t ring, pairs;
+};
+constexpr uint32_t kWireMagic = 0xB2001BC0u;
+std::string wire_path(uint32_t cookie, uint32_t qpn) {
+  char b[96];
+  snprintf(b, sizeof b, "/dev/shm/b200wire-%08x-%08x", cookie, qpn);
+  return b;
+}
+
 bool reg_has(const void* p) {
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.reg_mu);
@@ -329,6 +357,8 @@ extern "C" int b200_init(int device) {
       !halloc((void**)&r.h_scan_count, sizeof(uint32_t) * 4) ||
       !halloc((void**)&r.h_scan_ready, sizeof(int32_t) * kMaxPairs))
     return -1;
+  r.ipc_wire = getenv("B200_IPC_WIRE") ? env_long("B200_IPC_WIRE", 0) != 0 : env_long("WORLD_SIZE", 1) > 1;
+  if (r.ipc_wire && !CU_OK(cudaIpcGetMemHandle(&r.pairs_handle, r.d_pairs))) return -1;
   r.free_slots.clear();
   for (int i = kMaxPairs - 1; i >= 0; i--) r.free_slots.push_back(i);
   r.cookie = (uint32_t)getpid() * 2654435761u ^ (uint32_t)(uintptr_t)&r;
@@ -588,6 +618,26 @@ extern "C" void b200_pair_init(b200_pair* p) {
   p->self.ring_buffer_size = cap;  // "used to check peer has the same size", pair.cc:107
   r.by_qpn[p->self.qpn] = p;
   p->peer_local = nullptr;
+  p->remote = false;
+  if (r.ipc_wire) {
+    WireDesc d{};
+    d.magic = kWireMagic;
+    d.psn = p->self.psn;
+    d.dev = r.dev;
+    d.slot = p->slot;
+    d.cap = cap;
+    d.pairs = r.pairs_handle;
+    if (CU_OK(cudaIpcGetMemHandle(&d.ring, p->ring))) {
+      p->wire_file = wire_path(r.cookie, p->self.qpn);
+      const std::string tmp = p->wire_file + ".tmp";
+      int fd = open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0600);
+      if (fd >= 0) {
+        const bool okw = write(fd, &d, sizeof d) == (ssize_t)sizeof d;
+        close(fd);
+        if (okw) rename(tmp.c_str(), p->wire_file.c_str());
+      }
+    }
+  }
   p->error.clear();
   eventfd_t junk;
   (void)eventfd_read(p->wakeup_fd, &junk);
@@ -623,9 +673,66 @@ extern "C" int b200_pair_connect(b200_pair* p, const void* peer48, size_t n) {
   }
   uint32_t cookie;
   memcpy(&cookie, p->peer.gid, 4);
+  if (cookie != r.cookie) {
+    // ---- nvlink wire: the peer is another process on this box (one process per GPU)
+    WireDesc d{};
+    const std::string path = wire_path(cookie, p->peer.qpn);
+    int fd = open(path.c_str(), O_RDONLY);
+    const bool got = fd >= 0 && read(fd, &d, sizeof d) == (ssize_t)sizeof d;
+    if (fd >= 0) close(fd);
+    if (!got || d.magic != kWireMagic || d.psn != p->peer.psn || d.cap != p->cap) {
+      p->error = "peer is not reachable: no wire descriptor " + path +
+                 " (wires built: in-process loopback, CUDA-IPC/NVLink within one box; no NIC wire)";
+      set_err(p->error);
+      return 0;
+    }
+    cudaSetDevice(r.dev);
+    void* rring = nullptr;
+    if (!CU_OK(cudaIpcOpenMemHandle(&rring, d.ring, cudaIpcMemLazyEnablePeerAccess))) {
+      p->error = t_err;
+      return 0;
+    }
+    PairDev* table = nullptr;
+    auto pt = r.peer_tables.find(cookie);
+    if (pt != r.peer_tables.end()) {
+      table = pt->second;
+    } else {
+      void* tp = nullptr;
+      if (!CU_OK(cudaIpcOpenMemHandle(&tp, d.pairs, cudaIpcMemLazyEnablePeerAccess))) {
+        p->error = t_err;
+        cudaIpcCloseMemHandle(rring);
+        return 0;
+      }
+      table = (PairDev*)tp;
+      r.peer_tables[cookie] = table;
+    }
+    PairDev hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.ring = p->ring;
+    hd.cap = p->cap;
+    hd.peer_ring = (uint8_t*)rring;
+    hd.peer_credit = &table[d.slot].credit_head;
+    hd.mirror = p->mirror;
+    hd.peer_mirror = nullptr;
+    hd.status = B200_CONNECTED;
+    hd.max_sge = (uint32_t)r.cfg.max_sge;
+    hd.peer_slot = -1;
+    hd.wire = 1;  // system-scope fences: the ring is in another GPU's HBM, reached over NVLink
+    if (!write_setup(r, p, hd)) {
+      p->error = t_err;
+      p->status = B200_ERROR;
+      return 0;
+    }
+    p->remote = true;
+    p->remote_ring = (uint8_t*)rring;
+    p->remote_credit = hd.peer_credit;
+    p->peer_local = nullptr;
+    p->status = B200_CONNECTED;
+    return 1;
+  }
   auto it = r.by_qpn.find(p->peer.qpn);
-  if (cookie != r.cookie || it == r.by_qpn.end() || it->second->self.psn != p->peer.psn) {
-    p->error = "peer is not reachable: only the in-process loopback wire is built (no NIC / IPC wire)";
+  if (it == r.by_qpn.end() || it->second->self.psn != p->peer.psn) {
+    p->error = "peer is not reachable: unknown qpn on the in-process loopback wire";
     set_err(p->error);
     return 0;
   }
@@ -678,6 +785,25 @@ extern "C" void b200_pair_disconnect(b200_pair* p) {
     q->mirror->credit_head = st.remote_head;
     q->mirror->peer_exit = 1;
   }
+  if (p->remote) {
+    if (was_connected) {  // the same 16-byte status write, over NVLink into the peer's table
+      cudaStreamSynchronize(r.stream);
+      struct {
+        uint64_t remote_head;
+        uint32_t peer_exit, pad;
+      } st = {p->mirror->moving_head, 1, 0};
+      cudaMemcpyAsync(p->remote_credit, &st, 16, cudaMemcpyDefault, r.stream);
+      cudaStreamSynchronize(r.stream);
+    }
+    if (!r.svc_running.load()) cudaIpcCloseMemHandle(p->remote_ring);  // (device-wide sync: skipped beside the service)
+    p->remote = false;
+    p->remote_ring = nullptr;
+    p->remote_credit = nullptr;
+  }
+  if (!p->wire_file.empty()) {
+    unlink(p->wire_file.c_str());
+    p->wire_file.clear();
+  }
   uint32_t st = B200_DISCONNECTED;
   cudaMemcpyAsync(&r.d_pairs[p->slot].status, &st, 4, cudaMemcpyHostToDevice, r.stream);
   cudaStreamSynchronize(r.stream);
@@ -687,8 +813,19 @@ extern "C" void b200_pair_disconnect(b200_pair* p) {
   p->status = B200_DISCONNECTED;
 }
 
+// On the nvlink wire the bytes, the credit and the peer_exit flag are written by another GPU, so
+// nothing on this side knows when the mirror went stale: the wait-free answer comes from the
+// service kernel's poller when it runs, from a one-pair scan otherwise.
+static void refresh_remote(const b200_pair* cp) {
+  b200_pair* p = const_cast<b200_pair*>(cp);
+  if (!p->remote || p->status != B200_CONNECTED || R().svc_running.load()) return;
+  b200_pair* one[1] = {p};
+  b200_poller_scan(one, 1, nullptr);
+}
+
 extern "C" enum b200_status b200_pair_status(b200_pair* p) {
   if (!p) return B200_UNINITIALIZED;
+  refresh_remote(p);
   if (p->status == B200_CONNECTED && ((volatile PairMirror*)p->mirror)->peer_exit == 1)
     return B200_HALF_CLOSED;  // pair.cc:354-356
   return (enum b200_status)p->status;
@@ -701,17 +838,21 @@ extern "C" void b200_pair_consume_wakeup(b200_pair* p) {
   (void)eventfd_read(p->wakeup_fd, &v);
 }
 extern "C" int b200_pair_has_message(const b200_pair* p) {
-  return p && ((volatile PairMirror*)p->mirror)->has_message != 0;
+  if (!p) return 0;
+  refresh_remote(p);
+  return ((volatile PairMirror*)p->mirror)->has_message != 0;
 }
 extern "C" int b200_pair_has_pending_writes(const b200_pair* p) {
   return p && ((volatile PairMirror*)p->mirror)->partial_write != 0;
 }
 extern "C" uint64_t b200_pair_readable(const b200_pair* p) {
   if (!p || p->status != B200_CONNECTED) return 0;  // pair.cc:290-292
+  refresh_remote(p);
   return ((volatile PairMirror*)p->mirror)->readable;
 }
 extern "C" uint64_t b200_pair_writable(const b200_pair* p) {
   if (!p || !p->cap) return 0;
+  refresh_remote(p);
   volatile PairMirror* m = p->mirror;
   return writable_size(p->cap, m->credit_head, m->remote_tail);  // pair.cc:294-301
 }

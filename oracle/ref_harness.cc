@@ -308,6 +308,115 @@ static void* ref_worker_main(void* arg) {
   return nullptr;
 }
 
+// ------------------------------------------------------------ unary ping-pong
+// BASELINE config 3 at the pair level: `conns` connections served by `groups` client threads and
+// `groups` server threads (client i and server i own the same conns/groups connections).  A client
+// sends `msg_bytes` on a connection, spins on HasMessage, receives the echo, then moves to its
+// next connection; a server polls its connections round-robin (the Poller / busy-poll loop),
+// receives and echoes.  rtt_ns[c * iters + k] = round-trip time of iteration k on connection c.
+struct pp_worker {
+  int first_conn, n_conn, iters, warm, is_server;
+  uint64_t msg_bytes;
+  PairPollable** cli;
+  PairPollable** srv;
+  uint64_t* rtt_ns;
+  pthread_barrier_t* bar;
+  std::atomic<int>* stop;
+};
+
+static inline uint64_t now_ns() {
+  timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return static_cast<uint64_t>(t.tv_sec) * 1000000000ull + static_cast<uint64_t>(t.tv_nsec);
+}
+
+static void* pp_main(void* arg) {
+  auto* w = static_cast<pp_worker*>(arg);
+  std::vector<uint8_t> buf(w->msg_bytes), in(w->msg_bytes + 64);
+  for (uint64_t i = 0; i < w->msg_bytes; i++) buf[i] = static_cast<uint8_t>(i * 7 + w->first_conn);
+  hslice hs{buf.data(), w->msg_bytes};
+  std::vector<grpc_slice> gs;
+  to_grpc_slices(&hs, 1, gs);
+  pthread_barrier_wait(w->bar);
+  if (w->is_server) {
+    std::vector<uint64_t> got(w->n_conn, 0);
+    while (!w->stop->load(std::memory_order_relaxed)) {
+      for (int c = 0; c < w->n_conn; c++) {
+        PairPollable* p = w->srv[w->first_conn + c];
+        if (!p->HasMessage()) continue;
+        uint64_t n = p->Recv(in.data(), w->msg_bytes - got[c]);
+        got[c] += n;
+        if (got[c] == w->msg_bytes) {
+          got[c] = 0;
+          hslice es{in.data(), w->msg_bytes};
+          std::vector<grpc_slice> eg;
+          to_grpc_slices(&es, 1, eg);
+          uint64_t sent = 0;
+          while (sent < w->msg_bytes) sent += p->Send(eg.data(), 1, sent);
+        }
+      }
+    }
+  } else {
+    for (int k = -w->warm; k < w->iters; k++) {
+      for (int c = 0; c < w->n_conn; c++) {
+        PairPollable* p = w->cli[w->first_conn + c];
+        const uint64_t t0 = now_ns();
+        uint64_t sent = 0;
+        while (sent < w->msg_bytes) sent += p->Send(gs.data(), 1, sent);
+        uint64_t got = 0;
+        while (got < w->msg_bytes) {
+          while (!p->HasMessage()) {
+          }
+          got += p->Recv(in.data(), w->msg_bytes - got);
+        }
+        if (k >= 0) w->rtt_ns[static_cast<size_t>(w->first_conn + c) * w->iters + k] = now_ns() - t0;
+      }
+    }
+  }
+  return nullptr;
+}
+
+double ref_bench_pingpong(int conns, int groups, int iters, int warm, uint64_t msg_bytes, uint64_t ring_capacity,
+                          uint64_t* rtt_ns) {
+  ref_set_ring_kb(static_cast<uint32_t>(ring_capacity / 1024));
+  if (groups < 1) groups = 1;
+  if (groups > conns) groups = conns;
+  std::vector<PairPollable*> cli(conns), srv(conns);
+  for (int c = 0; c < conns; c++) {
+    cli[c] = static_cast<PairPollable*>(ref_pair_create());
+    srv[c] = static_cast<PairPollable*>(ref_pair_create());
+    ref_pair_connect(cli[c], srv[c]);
+  }
+  std::atomic<int> stop{0};
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, 2 * groups + 1);
+  std::vector<pthread_t> th(2 * groups);
+  std::vector<pp_worker> ws(2 * groups);
+  int base = 0;
+  for (int g = 0; g < groups; g++) {
+    int nc = conns / groups + (g < conns % groups ? 1 : 0);
+    ws[2 * g] = pp_worker{base, nc, iters, warm, 0, msg_bytes, cli.data(), srv.data(), rtt_ns, &bar, &stop};
+    ws[2 * g + 1] = pp_worker{base, nc, iters, warm, 1, msg_bytes, cli.data(), srv.data(), rtt_ns, &bar, &stop};
+    base += nc;
+    pthread_create(&th[2 * g], nullptr, pp_main, &ws[2 * g]);
+    pthread_create(&th[2 * g + 1], nullptr, pp_main, &ws[2 * g + 1]);
+  }
+  pthread_barrier_wait(&bar);
+  const uint64_t t0 = now_ns();
+  for (int g = 0; g < groups; g++) pthread_join(th[2 * g], nullptr);  // clients finish
+  const uint64_t t1 = now_ns();
+  stop.store(1);
+  for (int g = 0; g < groups; g++) pthread_join(th[2 * g + 1], nullptr);
+  pthread_barrier_destroy(&bar);
+  for (int c = 0; c < conns; c++) {
+    cli[c]->Disconnect();
+    srv[c]->Disconnect();
+    delete cli[c];
+    delete srv[c];
+  }
+  return 1e-9 * static_cast<double>(t1 - t0);
+}
+
 double ref_bench_stream(int conns, int threads, int warm, int msgs, uint64_t ring_capacity,
                         const uint64_t* lens, size_t nslices, uint64_t* delivered,
                         uint64_t* checksum) {

@@ -223,8 +223,20 @@ int ibv_post_send(ibv_qp* qp, ibv_send_wr* wr, ibv_send_wr** bad) {
     if (wr->opcode == IBV_WR_RDMA_WRITE) {
       uint8_t* dst = reinterpret_cast<uint8_t*>(wr->wr.rdma.remote_addr);
       for (int i = 0; i < wr->num_sge; i++) {
-        memcpy(dst, reinterpret_cast<void*>(wr->sg_list[i].addr), wr->sg_list[i].length);
-        dst += wr->sg_list[i].length;
+        // An HCA places an RDMA write in address order; a reader on another thread relies on the
+        // last word (a frame's footer, ring_buffer.cc:75-96) landing after everything before it.
+        // memcpy gives no such order, so the last 8 bytes of every SGE are stored separately.
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wr->sg_list[i].addr);
+        const uint32_t len = wr->sg_list[i].length;
+        if (len >= 8 && ((reinterpret_cast<uintptr_t>(dst) + len) & 7) == 0) {
+          memcpy(dst, src, len - 8);
+          uint64_t last;
+          memcpy(&last, src + len - 8, 8);
+          __atomic_store_n(reinterpret_cast<uint64_t*>(dst + len - 8), last, __ATOMIC_RELEASE);
+        } else {
+          memcpy(dst, src, len);
+        }
+        dst += len;
       }
       wc.opcode = IBV_WC_RDMA_WRITE;
     } else if (wr->opcode == IBV_WR_SEND_WITH_IMM || wr->opcode == IBV_WR_SEND) {

@@ -204,6 +204,7 @@ class Ref:
             ("ref_ring_write_frames", u64, [vp, u64, vp, C.POINTER(Slice), C.c_size_t, C.POINTER(C.c_int)]),
             ("ref_bench_stream", C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, u64, C.POINTER(u64), C.c_size_t,
                                               C.POINTER(u64), C.POINTER(u64)]),
+            ("ref_bench_pingpong", C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, u64, u64, C.POINTER(u64)]),
         ]:
             f = getattr(L, fname)
             f.restype = res
@@ -268,6 +269,12 @@ class Ref:
 
     def disconnect(self, p):
         self.L.ref_pair_disconnect(p)
+
+    def bench_pingpong(self, conns, groups, iters, warm, msg_bytes, ring_capacity):
+        """Returns (wall seconds, rtt_ns[conns, iters]) of the reference's own Send/HasMessage/Recv ping-pong."""
+        rtt = np.zeros(conns * iters, dtype=np.uint64)
+        t = self.L.ref_bench_pingpong(conns, groups, iters, warm, msg_bytes, ring_capacity, _u64p(rtt))
+        return t, rtt.reshape(conns, iters)
 
     def bench_stream(self, conns, threads, warm, msgs, ring_capacity, lens):
         lens = np.ascontiguousarray(lens, dtype=np.uint64)
