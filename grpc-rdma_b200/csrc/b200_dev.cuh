@@ -124,16 +124,18 @@ constexpr uint32_t kStError = 5;
 // continuously, keeps the host-visible mirrors current and appends readiness CHANGES to the
 // ready ring (warp-aggregated: one atomic per warp).
 constexpr uint32_t kSvcSend = 1, kSvcRecv = 2, kSvcStop = 3;
-struct __align__(64) SvcCmd {
+constexpr uint32_t kSvcInline = 5;  // slices carried inside the command (a unary call has 2-4)
+struct __align__(128) SvcCmd {
   uint32_t seq;      // command number, written last by the host
   uint32_t op;       // kSvcSend / kSvcRecv / kSvcStop
   int32_t slot;
   uint32_t flags;    // B200_BATCH_*
-  uint64_t ptr;      // send: SliceDev* (GPU-addressable)   recv: destination
+  uint64_t ptr;      // send: SliceDev* (GPU-addressable; unused when n <= kSvcInline)   recv: destination
   uint64_t n;        // send: nslices                        recv: capacity
   uint64_t byte_idx;
-  uint64_t _pad[3];
+  SliceDev inl[kSvcInline];  // send: the slice list itself when it is short -- no second trip over PCIe
 };
+static_assert(sizeof(SvcCmd) == 128, "one command = one 128-byte line");
 struct __align__(32) SvcDone {
   uint64_t bytes, calls;
   uint32_t seq;      // = SvcCmd.seq once the op is finished and its bytes are visible

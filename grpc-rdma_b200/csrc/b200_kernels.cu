@@ -386,7 +386,8 @@ __device__ __noinline__ void send_produce_segment(const SendOpDev& op, const Pai
     // value moved, i.e. when this call may write into space that was just cleared.
     const uint64_t rh = ld_volatile_u64(&P->credit_head);
     if (rh != S.last_rh) {
-      __threadfence_system();
+      if (P->wire != 0) __threadfence_system();
+      else __threadfence();  // loopback wire: the credit writer is a kernel on this GPU
       S.last_rh = rh;  // every lane writes the same value
     }
     const uint64_t cur = S.cur, bidx = S.bidx;
@@ -1207,14 +1208,13 @@ k_service(PairDev* __restrict__ pairs, SvcCmd* cmds, SvcDone* done, SvcPollState
       uint32_t backoff = 0;
       while (ld_acquire_u32(&cmd->seq) != expect)  // one PCIe read per poll
         if (++backoff > 64) __nanosleep(100);
-      s_cmd.op = *(volatile uint32_t*)&cmd->op;
-      s_cmd.slot = *(volatile int32_t*)&cmd->slot;
-      s_cmd.flags = *(volatile uint32_t*)&cmd->flags;
-      s_cmd.ptr = *(volatile uint64_t*)&cmd->ptr;
-      s_cmd.n = *(volatile uint64_t*)&cmd->n;
-      s_cmd.byte_idx = *(volatile uint64_t*)&cmd->byte_idx;
       s_res.bytes = 0;
       s_res.calls = 0;
+    }
+    __syncthreads();
+    if (tid < 8) {  // the whole 128-byte command in one trip: 8 lanes x 16 bytes
+      const uint4 v = ld_ring16(reinterpret_cast<const uint4*>(cmd) + tid);
+      reinterpret_cast<uint4*>(&s_cmd)[tid] = v;
     }
     __syncthreads();
     const uint32_t opc = s_cmd.op;
@@ -1223,7 +1223,7 @@ k_service(PairDev* __restrict__ pairs, SvcCmd* cmds, SvcDone* done, SvcPollState
       SendOpDev op;
       op.slot = s_cmd.slot;
       op.flags = s_cmd.flags;
-      op.slices = reinterpret_cast<const SliceDev*>(s_cmd.ptr);
+      op.slices = s_cmd.n <= kSvcInline ? s_cmd.inl : reinterpret_cast<const SliceDev*>(s_cmd.ptr);
       op.nslices = s_cmd.n;
       op.byte_idx = s_cmd.byte_idx;
       send_body(pairs, op, &s_res, pipe, stage_mem, phase_bits);
@@ -1235,7 +1235,9 @@ k_service(PairDev* __restrict__ pairs, SvcCmd* cmds, SvcDone* done, SvcPollState
       op.cap = s_cmd.n;
       recv_body(pairs, op, &s_res, pipe, stage_mem, phase_bits);
     }
-    __threadfence_system();  // every thread's bytes (ring, host destination, mirrors) before the answer
+    // every byte this op produced must be visible before the answer: a Recv may have scattered into
+    // host memory from any mover; a Send only wrote host memory (the mirrors) from thread 0
+    if (opc == kSvcRecv || tid == 0) __threadfence_system();
     __syncthreads();
     if (tid == 0) {
       volatile SvcDone* vd = dn;

@@ -1055,6 +1055,7 @@ static uint64_t svc_send(Runtime& r, b200_pair* p, const b200_slice* slices, siz
     w.slices[nsl].len = rest;
     nsl++;
   }
+  if (nsl <= kSvcInline) memcpy(r.svc_cmds[wi].inl, w.slices, sizeof(SliceDev) * nsl);
   uint64_t bytes = 0;
   if (!svc_call(r, w, wi, kSvcSend, p->slot, (uint64_t)(uintptr_t)w.slices, nsl, byte_idx, &bytes)) {
     p->error = t_err;
