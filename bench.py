@@ -228,7 +228,8 @@ def main():
     del i, row, offs
     dst = torch.zeros(conns * total, dtype=torch.uint8, device=dev)
 
-    def build_batches(src_ptr, dst_ptr, extra_flags=0):
+    def build_batches(src_ptr, dst_ptr, extra_flags=0, dst_stride=None):
+        dst_stride = dst_stride or total
         sops, rops, keep = [], [], []
         for c in range(conns):
             off, sl = 0, []
@@ -238,7 +239,7 @@ def main():
             arr = pkg.make_slices(sl)
             keep.append(arr)
             sops.append((pairs[c][0], arr, len(lens), 0))
-            rops.append((pairs[c][1], dst_ptr + c * total, total))
+            rops.append((pairs[c][1], dst_ptr + c * dst_stride, total))
         fl = pkg.UNTIL_BLOCKED | extra_flags
         return pkg.Batch("send", sops, fl), pkg.Batch("recv", rops, fl), keep
 
@@ -449,14 +450,18 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
     delivered bytes must land in pinned host memory, every step, inside the timed region."""
     import torch
     nbytes = conns * total
+    # Source slices sit wherever the application left them (here back to back: not even 16-byte aligned).
+    # Destination windows are what the endpoint itself allocates for a read (rdma_bp_posix.cc:308-317):
+    # one pinned slice per connection, 256-byte aligned like every b200_mem_alloc_host block.
+    dstride = (total + 255) // 256 * 256
     hsrc = L.b200_mem_alloc_host(nbytes)
-    hdst = L.b200_mem_alloc_host(nbytes)
+    hdst = L.b200_mem_alloc_host(conns * dstride)
     if not hsrc or not hdst:
         return {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "pinned allocation failed: " + pkg.last_error()}
     import numpy as np
     hs = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(hsrc))
-    hd = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(hdst))
+    hd = np.ctypeslib.as_array((C.c_uint8 * (conns * dstride)).from_address(hdst)).reshape(conns, dstride)
     i = np.arange(total, dtype=np.uint64)
     for c in range(conns):
         hs[c * total:(c + 1) * total] = ((i * np.uint64(40503) >> np.uint64(5)) + np.uint64(17 * c)).astype(np.uint8)
@@ -466,14 +471,14 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
     for mode in modes:
         if mode == "zerocopy":
             # kernels address the pinned host slices / destinations directly: bytes cross PCIe once each way
-            bs, br, keep = build_batches(hsrc, hdst, pkg.ZEROCOPY)
+            bs, br, keep = build_batches(hsrc, hdst, pkg.ZEROCOPY, dstride)
 
             def step():
                 bs.launch(sh)
                 br.launch(sh)
         else:
             # the library's host-staged path: per lane H2D -> k_send ... k_recv -> D2H on internal streams
-            bs, br, keep = build_batches(hsrc, hdst)
+            bs, br, keep = build_batches(hsrc, hdst, 0, dstride)
 
             def step():
                 bs.launch(None)
@@ -482,7 +487,7 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
         step()
         L.b200_lanes_join(None)
         torch.cuda.synchronize()
-        ok = bool(np.array_equal(hs, hd))
+        ok = bool(np.array_equal(hs.reshape(conns, total), hd[:, :total]))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if dist is not None:
             dist.barrier()

@@ -882,6 +882,8 @@ extern "C" int b200_pair_copy_ring(b200_pair* p, void* host_dst, uint64_t cap) {
   return CU_OK(cudaMemcpy(host_dst, p->ring, p->cap, cudaMemcpyDeviceToHost)) ? 0 : -1;
 }
 
+static void refresh_remote(const b200_pair* cp);
+
 // ================================================================== service
 //
 // The persistent kernel of the unary path: worker CTAs take Send / Recv commands from pinned
@@ -1099,9 +1101,26 @@ static bool ensure_bounce(uint8_t** buf, uint64_t* cap, uint64_t need) {
   return true;
 }
 
+// The endpoint re-enters Send from the poll loop for as long as a write is pending, whether or not
+// the peer has returned credit (poller.cc:83, rdma_bp_posix.cc:527-557).  On the CPU that is a cheap
+// call; here it would be a launch per spin.  When the host-visible mirror already shows that the
+// call cannot accept a byte (no credit for even one frame and the partial-write flag already set),
+// the answer and the resulting state are exactly those of the kernel, so no kernel runs.
+static bool send_is_a_no_op(const b200_pair* p) {
+  volatile PairMirror* m = p->mirror;
+  if (!m->partial_write) return false;
+  const uint64_t fr = free_size(p->cap, m->credit_head, m->remote_tail);
+  const uint64_t lim = p->cap / 2 < fr ? p->cap / 2 : fr;
+  return calc_writable(lim) == 0;
+}
+
 extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
   if (!p || !ensure_init()) return 0;
   Runtime& r = R();
+  if (p->status == B200_CONNECTED && n) {
+    refresh_remote(p);
+    if (send_is_a_no_op(p)) return 0;
+  }
   if (r.svc_running.load()) {
     if (p->status != B200_CONNECTED || n == 0) return 0;
     if (((volatile PairMirror*)p->mirror)->peer_exit == 1) return 0;
@@ -1167,6 +1186,8 @@ extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_
 extern "C" uint64_t b200_pair_recv(b200_pair* p, void* dst, uint64_t cap) {
   if (!p || !ensure_init()) return 0;
   Runtime& r = R();
+  // same reasoning for a Recv on a ring the mirror shows empty: it delivers nothing, changes nothing
+  if (p->status == B200_CONNECTED && !p->remote && ((volatile PairMirror*)p->mirror)->has_message == 0) return 0;
   if (r.svc_running.load()) {
     if (p->status != B200_CONNECTED || cap == 0) return 0;
     return svc_recv(r, p, dst, cap);
@@ -1222,11 +1243,41 @@ static int lane_of(const b200_pair* p) {
   return (key >> shift) % nl;  // both ends of a loopback connection share a lane: per-connection order
 }
 
+constexpr size_t kDmaAlign = 4096;
+
 static size_t stage_place(size_t& cursor, const void* host_ptr, size_t bytes) {
-  // keep the host buffer's alignment modulo 256 so the kernels see the same (mis)alignment
-  size_t off = ((cursor + 255) & ~(size_t)255) + ((uintptr_t)host_ptr & 255);
+  // keep the host buffer's alignment modulo 4 KiB: the kernels see the same (mis)alignment and
+  // the DMA engine sees page-aligned transfers on both sides
+  size_t off = ((cursor + kDmaAlign - 1) & ~(kDmaAlign - 1)) + ((uintptr_t)host_ptr & (kDmaAlign - 1));
   cursor = off + bytes;
   return off;
+}
+
+// A DMA copy whose HOST address is not 256-byte aligned runs at ~3/4 of the PCIe rate when both
+// directions are busy (measured: 35.5 vs 45 GB/s per direction; the device address and the size do
+// not matter; splitting off small edge copies costs more than it saves -- profiles/r1k_pcie_alignment.txt).
+//   H2D: the transfer is widened to the enclosing 256-byte blocks of the host buffer (a few extra bytes
+//        of the same pinned page land in the staging arena next to the slice and are never read);
+//   D2H: must be exact, so destinations should be 256-byte aligned -- the endpoint allocates its read
+//        slices itself (rdma_bp_posix.cc:308-317), from b200_mem_alloc_host they are.
+constexpr size_t kHostDmaAlign = 256;
+static void push_h2d(std::vector<CopyRun>& out, uint8_t* stage, const uint8_t* src, size_t bytes) {
+  if (!bytes) return;
+  // only the START needs the alignment (the size does not matter), and only inside the registered
+  // range the bytes belong to: the driver rejects a copy that leaves it
+  size_t lead = (uintptr_t)src & (kHostDmaAlign - 1);
+  if (lead) {
+    Runtime& r = R();
+    std::lock_guard<std::mutex> lk(r.reg_mu);
+    auto it = r.reg_ranges.upper_bound((uintptr_t)src);
+    if (it == r.reg_ranges.begin()) {
+      lead = 0;  // memory registered by someone else: its base is unknown
+    } else {
+      --it;
+      if ((uintptr_t)src >= it->first + it->second || (uintptr_t)src - lead < it->first) lead = 0;
+    }
+  }
+  out.push_back({stage - lead, src - lead, lead + bytes});
 }
 
 static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int flags) {
@@ -1324,10 +1375,10 @@ static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int 
       off += o.nslices;
     }
     if (ok && b->staged) {
-      ok = CU_OK(cudaMalloc(&b->d_stage, cursor + 256));
+      ok = CU_OK(cudaMalloc(&b->d_stage, cursor + kDmaAlign));
       for (size_t q = 0; ok && q < total_slices; q++)
         if (hs[q].len) hs[q].ptr = b->d_stage + stage_off[q];
-      for (const Run& rn : runs) b->lanes[rn.lane].copies.push_back({b->d_stage + rn.stage, rn.src, rn.bytes});
+      for (const Run& rn : runs) push_h2d(b->lanes[rn.lane].copies, b->d_stage + rn.stage, rn.src, rn.bytes);
     }
     ok = ok && CU_OK(cudaMemcpy(b->d_slices, hs.data(), sizeof(SliceDev) * hs.size(), cudaMemcpyHostToDevice)) &&
          CU_OK(cudaMemcpy(b->d_ops, h.data(), sizeof(SendOpDev) * (nops ? nops : 1), cudaMemcpyHostToDevice));
@@ -1345,7 +1396,7 @@ static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int 
       if (b->staged && o.cap) place[k] = stage_place(cursor, o.dst, o.cap);
     }
     if (ok && b->staged) {
-      ok = CU_OK(cudaMalloc(&b->d_stage, cursor + 256));
+      ok = CU_OK(cudaMalloc(&b->d_stage, cursor + kDmaAlign));
       for (size_t k = 0; ok && k < nops; k++) {
         const b200_recv_op& o = rops[b->perm[k]];
         if (!o.cap) continue;
