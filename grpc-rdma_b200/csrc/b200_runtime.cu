@@ -368,6 +368,8 @@ extern "C" int b200_init(int device) {
     atexit([] {  // poller threads joined and the persistent kernel gone before static destruction
       b200_poller_shutdown();
       b200_service_stop();
+      for (b200_pair* p : R().all_pairs)  // wire descriptors of pairs nobody disconnected
+        if (!p->wire_file.empty()) unlink(p->wire_file.c_str());
     });
   }
   r.inited = true;
