@@ -38,9 +38,10 @@ B200_HD uint64_t writable_size(uint64_t cap, uint64_t head, uint64_t tail) {
   return f > kReserved ? f - kReserved : 0;
 }
 
-// Host-visible mirror of one pair (pinned, GPU-mapped).  Kernels refresh it at
-// the end of every op that touches the pair so that HasMessage /
-// HasPendingWrites / get_status stay wait-free host reads (pair.cc:288-303).
+// Host-visible mirror of one pair (pinned, GPU-mapped).  Kernels refresh the
+// fields they own at the end of every op that touches the pair (posted writes
+// only) so that HasMessage / HasPendingWrites / get_status stay wait-free host
+// reads (pair.cc:288-303).
 struct PairMirror {
   uint64_t head, moving_head, remain, acc;
   uint64_t remote_tail, credit_head;
@@ -48,7 +49,7 @@ struct PairMirror {
   uint32_t partial_write;  // HasPendingWrites()
   uint32_t peer_exit;      // status_report.peer_exit seen by this pair
   uint32_t has_message;    // HasMessage()
-  uint32_t seq;            // bumped on every refresh
+  uint32_t _reserved;
 };
 
 // One connection endpoint in HBM.  Three blocks with distinct writers:
