@@ -34,7 +34,7 @@ CONNS = 256
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--conns", type=int, default=CONNS)
@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-unary", action="store_true")
+    ap.add_argument("--msgs-per-step", type=int, default=1, help="experiment: messages per connection per step")
     ap.add_argument("--unary-bytes", type=int, default=1024)
     ap.add_argument("--unary-iters", type=int, default=2000)
     ap.add_argument("--service-workers", type=int, default=16)
@@ -56,8 +57,11 @@ def parse():
 # ----------------------------------------------------------------------------- clocks
 
 class ClockSampler:
-    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampled DURING the timed regions (B200_PROFILING.md clocks line).  The device-resident
+    timed region of the default run lasts ~0.1 s, so the sampler runs at 20 ms from before the warm-up to
+    after the e2e region and every row carries its own timestamp; `window(t0, t1)` reports the rows that
+    fall inside one timed region (wall clock)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -68,28 +72,40 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
             self.proc = None
 
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = time.time()
+            self.rows.append((ts, r[1:]))
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+            return
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+
+    def window(self, t0, t1, label):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not (t0 - 0.02 <= ts <= t1 + 0.02):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -100,7 +116,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "region": label}
 
 
 # ------------------------------------------------------------------------ CPU baseline
@@ -212,7 +228,7 @@ def main():
     pkg.config_set("GRPC_RDMA_MAX_SGE", 30)
 
     conns, msg = args.conns, args.msg_bytes
-    lens = pkg.chttp2_slice_lens(msg)
+    lens = pkg.chttp2_slice_lens(msg) * args.msgs_per_step
     total = sum(lens)                       # bytes the endpoint moves per message (payload + HTTP/2 framing)
     tx_alg, rx_alg = pkg.frame_hbm_bytes(lens)
     dev = torch.device("cuda", local)
@@ -277,6 +293,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -286,11 +304,10 @@ def main():
     # ---- timed region: device resident
     K = args.steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    sampler = ClockSampler(local)
     launches0 = L.b200_launch_count()
     barrier()
-    sampler.start()
     t_wall0 = time.perf_counter()
+    t_region0 = time.time()
     for k in range(K):
         ev[k][0].record(stream)
         bs.launch(sh)
@@ -299,7 +316,7 @@ def main():
         ev[k][2].record(stream)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    t_region1 = time.time()
     barrier()
     launches = L.b200_launch_count() - launches0
     t_dev_ms = ev[0][0].elapsed_time(ev[K - 1][2])
@@ -312,7 +329,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev_ms = float(t.item())
 
-    n_msgs = world * conns * K
+    n_msgs = world * conns * K * args.msgs_per_step
     gbs = n_msgs * msg / (t_dev_ms * 1e-3) / 1e9
     peaks = {}
     try:
@@ -337,6 +354,17 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist if world > 1 else None, dev, stream, sh,
                       build_batches)
+
+    t_e2e1 = time.time()
+    sampler.stop()
+    clocks = sampler.window(t_region0, t_region1, "device-resident timed region")
+    if e2e is not None:
+        w = e2e.pop("_wall", None) or (t_region1, t_e2e1)
+        e2e["clocks"] = sampler.window(w[0], w[1], "e2e timed region")
+    if not clocks.get("samples") and e2e is not None:
+        # a very short timed region can fall between two 20 ms samples: say so and show the e2e window
+        clocks = dict(e2e["clocks"], note="no sample fell inside the %.0f ms device-resident region; "
+                                           "these are the samples of the e2e region that follows it" % ((t_region1 - t_region0) * 1e3))
 
     unary = None
     if rank == 0 and not args.no_unary:
@@ -492,6 +520,7 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+        tw0 = time.time()
         e0.record(stream)
         L.b200_lanes_fork(sh)        # lanes start after e0 ...
         for _ in range(K):
@@ -499,22 +528,29 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
         L.b200_lanes_join(sh)        # ... and e1 waits for every lane
         e1.record(stream)
         torch.cuda.synchronize()
+        tw1 = time.time()
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         ok = ok and bs.results(sh) == [total] * conns and br.results(sh) == [total] * conns
-        results[mode] = {"GBps": world * conns * K * msg / (ms * 1e-3) / 1e9, "ms_per_step": ms / K, "intact": ok}
+        results[mode] = {"GBps": world * conns * K * msg / (ms * 1e-3) / 1e9, "ms_per_step": ms / K, "intact": ok,
+                         "_wall": (tw0, tw1)}
         bs.destroy()
         br.destroy()
     L.b200_mem_free_host(hsrc)
     L.b200_mem_free_host(hdst)
     best = max((m for m in results if results[m]["intact"]), key=lambda m: results[m]["GBps"], default=None)
     if best is None:
+        for m in results:
+            results[m].pop("_wall", None)
         return {"value": None, "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "note": "e2e verification failed", "modes": results}
-    return {"value": results[best]["GBps"], "unit": "GB/s", "h2d_bytes_per_step": nbytes,
+    wall = results[best].pop("_wall")
+    for m in results:
+        results[m].pop("_wall", None)
+    return {"_wall": wall, "value": results[best]["GBps"], "unit": "GB/s", "h2d_bytes_per_step": nbytes,
             "d2h_bytes_per_step": nbytes, "mode": best, "steps": K, "ms_per_step": results[best]["ms_per_step"],
             "modes": results,
             "note": "slices and destinations are pinned host memory; per step every payload byte crosses PCIe "
