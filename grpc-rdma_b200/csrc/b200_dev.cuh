@@ -76,11 +76,12 @@ struct __align__(128) PairDev {
   uint64_t acc;          // PairPollable::internal_read_size_
   uint64_t remote_tail;  // PairPollable::remote_tail_
   uint32_t partial_write;
-  uint32_t _pad0;
+  uint32_t mlock;        // serialises "read the device truth, write the mirror" when ops of the two
+                         // ends run concurrently (kFlagConcurrent)
   // ---- credit (offset 112, 16-byte aligned)
   uint64_t credit_head;  // status_report.remote_head
   uint32_t credit_exit;  // status_report.peer_exit
-  uint32_t _pad1;
+  uint32_t _pad1;        // covered by the peer's 16-byte status write: nothing of ours may live here
 };
 static_assert(sizeof(PairDev) == 128, "PairDev is one 128-byte line");
 
@@ -111,6 +112,7 @@ struct OpResult {
 };
 
 constexpr uint32_t kFlagUntilBlocked = 0x1;
+constexpr uint32_t kFlagConcurrent = 0x8;  // B200_BATCH_CONCURRENT
 constexpr uint32_t kEvReadable = 0x1;
 constexpr uint32_t kEvWritable = 0x4;
 

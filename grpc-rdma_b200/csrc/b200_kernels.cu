@@ -213,9 +213,26 @@ __device__ __forceinline__ void publish_mirror_tx(PairMirror* m, const PairDev* 
   if (m == nullptr) return;
   volatile PairMirror* vm = m;
   vm->remote_tail = P->remote_tail;
-  vm->credit_head = P->credit_head;
+  vm->credit_head = *(volatile const uint64_t*)&P->credit_head;
   vm->partial_write = P->partial_write;
-  vm->peer_exit = P->credit_exit;
+  vm->peer_exit = *(volatile const uint32_t*)&P->credit_exit;
+}
+
+// A pair's readiness fields are written by its own Recv and by the peer's Send (which lands the
+// bytes); its credit field by its own Send and by the peer's Recv (which returns the credit).  When
+// the two ends' ops can run at the same time (the service kernel's workers, or batches on separate
+// streams with B200_BATCH_CONCURRENT) each "read the device truth, write the mirror" runs under the
+// pair's lock and is made visible system-wide before the lock is released, so the mirror always ends
+// up with the newest view and the host never waits on a readiness that was overwritten by an older one.
+__device__ __forceinline__ void mirror_lock(PairDev* P, bool on) {
+  if (!on) return;
+  while (atomicCAS(&P->mlock, 0u, 1u) != 0u) __nanosleep(64);
+  __threadfence();
+}
+__device__ __forceinline__ void mirror_unlock(PairDev* P, bool on) {
+  if (!on) return;
+  __threadfence_system();
+  atomicExch(&P->mlock, 0u);
 }
 
 // =========================================================================
@@ -629,17 +646,22 @@ __device__ __forceinline__ void send_body(PairDev* __restrict__ pairs, const Sen
     P->partial_write = PS.partial;
     result->bytes = PS.written_total;
     result->calls = PS.ncalls;
+    const bool conc = (op.flags & kFlagConcurrent) != 0;
+    mirror_lock(P, conc);
     publish_mirror_tx(P->mirror, P);
+    mirror_unlock(P, conc);
     // loopback wire: the peer lives in this table, refresh its readiness hint
     if (P->peer_slot >= 0 && PS.written_total) {
       PairDev* Q = &pairs[P->peer_slot];
       if (Q->mirror) {
         uint32_t hm;
         uint64_t rd;
+        mirror_lock(Q, conc);
         rx_probe<false>(Q->ring, Q->cap, *(volatile uint64_t*)&Q->head, *(volatile uint64_t*)&Q->remain, hm, rd);
         volatile PairMirror* vm = Q->mirror;
         vm->has_message = hm;
         vm->readable = rd;
+        mirror_unlock(Q, conc);
       }
     }
   }
@@ -1032,8 +1054,12 @@ __device__ __forceinline__ void recv_body(PairDev* __restrict__ pairs, const Rec
     const bool done = ctl.op_done != 0;
     if (tid == 0 && credit) {
       // updateStatus, pair.cc:624-641: 16-byte status_report to the peer
+      const bool conc = (op.flags & kFlagConcurrent) != 0 && P->peer_slot >= 0;
+      PairDev* Q = conc ? &pairs[P->peer_slot] : nullptr;
+      if (conc) mirror_lock(Q, true);
       st_release_v2u64(P->peer_credit, SS.credit_val, 0);
       if (P->peer_mirror) ((volatile PairMirror*)P->peer_mirror)->credit_head = SS.credit_val;
+      if (conc) mirror_unlock(Q, true);
       SS.credit_flag = 0;
     }
     __syncthreads();
@@ -1048,8 +1074,11 @@ __device__ __forceinline__ void recv_body(PairDev* __restrict__ pairs, const Rec
     result->calls = SS.ncalls;
     uint32_t hm;
     uint64_t rd;
+    const bool conc = (op.flags & kFlagConcurrent) != 0;
+    mirror_lock(P, conc);
     rx_probe<false>(ring, cap, SS.head, SS.remain, hm, rd);
     publish_mirror_rx(P->mirror, P, hm, rd);
+    mirror_unlock(P, conc);
   }
 }
 

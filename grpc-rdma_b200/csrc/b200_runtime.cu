@@ -1002,7 +1002,7 @@ static bool svc_call(Runtime& r, Runtime::SvcWorker& w, int wi, uint32_t op, int
   volatile SvcDone* d = &r.svc_done[wi];
   c->op = op;
   c->slot = slot;
-  c->flags = B200_BATCH_ONE_CALL;
+  c->flags = B200_BATCH_ONE_CALL | B200_BATCH_CONCURRENT;  // the two ends' workers run side by side
   c->ptr = ptr;
   c->n = n;
   c->byte_idx = byte_idx;
@@ -1335,7 +1335,7 @@ static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int 
   } else {
     for (size_t i = 0; i < nops; i++) b->perm[i] = (int)i;
   }
-  const uint32_t kflags = (uint32_t)(flags & B200_BATCH_UNTIL_BLOCKED);
+  const uint32_t kflags = (uint32_t)(flags & (B200_BATCH_UNTIL_BLOCKED | B200_BATCH_CONCURRENT));
   if (ok && kind == 0) {
     size_t total_slices = 0;
     for (size_t i = 0; i < nops; i++) total_slices += sops[i].nslices;

@@ -213,6 +213,12 @@ void b200_service_stats(uint64_t out[4]);
 #define B200_BATCH_UNTIL_BLOCKED 0x1
 #define B200_BATCH_ASYNC 0x2 /* do not synchronise; results valid after stream sync */
 #define B200_BATCH_ZEROCOPY 0x4 /* pinned HOST buffers are dereferenced by the kernels over PCIe */
+/* Sends and Recvs of the SAME connection may run at the same time (batches launched on separate
+ * streams without an ordering between them): the kernels then update the host-visible mirrors under a
+ * per-pair device lock so that an older readiness / credit view can never overwrite a newer one.
+ * The service kernel always works this way; the library's own lanes order the two ends by events and
+ * do not need it. */
+#define B200_BATCH_CONCURRENT 0x8
 /*
  * Where the bytes live decides the path of a batch:
  *   device memory        kernels work in place (one launch per batch);

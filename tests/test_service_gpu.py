@@ -136,3 +136,24 @@ def test_ready_ring_drives_the_background_poller(svc):
     assert b.status() == 3
     L.b200_poller_remove(b.h)
     b.disconnect()
+
+
+def test_endpoint_echo_with_the_service_running(svc):
+    """The whole BPEV loop without a single launch: endpoint state machine + busy-poll/epoll engine
+    (b200_endpoint.cc) over pairs whose Send / Recv are executed by the resident kernel and whose
+    readiness comes from its poller CTA (eventfd kicks through the ready ring)."""
+    import endpoint_lib
+    pkg, L = svc, svc.lib()
+    D, _ = endpoint_lib.load(pkg, need_oracle=False)
+    pkg.config_set("GRPC_RDMA_RING_BUFFER_SIZE_KB", 1024)
+    launches = L.b200_launch_count()
+    ops0 = _stats(L)[0]
+    nbytes = C.c_uint64(0)
+    # client and server threads, busy-poll window 100 us, background poller on
+    assert D.drv_echo(None, 12, 1_500_000, 99, 100, 1, 1, C.byref(nbytes)) == 0
+    assert nbytes.value > 0
+    assert _stats(L)[0] > ops0 + 100            # the calls went through the service
+    assert L.b200_launch_count() == launches    # and nothing was launched
+    # conformance shape: 100 kB writes of 8192-byte slices, byte ramp checked on the reader
+    assert D.drv_read_and_write(None, 2_000_000, 100_000, 8192, 0, 100, 0, None) == 0
+    assert L.b200_launch_count() == launches
