@@ -1265,8 +1265,9 @@ k_service(PairDev* __restrict__ pairs, SvcCmd* cmds, SvcDone* done, SvcPollState
       recv_body(pairs, op, &s_res, pipe, stage_mem, phase_bits);
     }
     // every byte this op produced must be visible before the answer: a Recv may have scattered into
-    // host memory from any mover; a Send only wrote host memory (the mirrors) from thread 0
-    if (opc == kSvcRecv || tid == 0) __threadfence_system();
+    // host memory from any mover; a Send only wrote host memory (the mirrors) from thread 0, under the
+    // mirror lock, whose release already fenced system-wide
+    if (opc == kSvcRecv) __threadfence_system();
     __syncthreads();
     if (tid == 0) {
       volatile SvcDone* vd = dn;
