@@ -52,15 +52,17 @@ class PairPollable {  // pair.h:82-271
     return b200_pair_connect(p_, peer.data(), peer.size()) == 1;
   }
   uint64_t Send(grpc_slice* slices, size_t n, size_t byte_idx) {             // pair.cc:645
-    constexpr size_t kMax = 128;  // MAX_WRITE_IOVEC, rdma_bp_posix.cc:378-381
-    b200_slice flat[kMax];
-    uint64_t rest = 0;
-    size_t m = n < kMax ? n : kMax;
-    for (size_t i = 0; i < m; i++) flat[i] = {GRPC_SLICE_START_PTR(slices[i]), GRPC_SLICE_LENGTH(slices[i])};
-    // slices beyond what one call looks at only count towards total_slice_size (pair.cc:661-664)
-    for (size_t i = m; i < n; i++) rest += GRPC_SLICE_LENGTH(slices[i]);
-    if (rest && m == kMax) flat[kMax - 1].len += 0;  // (a Send call never looks past max_sge slices)
-    return b200_pair_send(p_, flat, m, byte_idx);
+    // every slice is passed on: a call looks at <= max_sge of them, but the rest counts towards
+    // total_slice_size and therefore towards partial_write_ (pair.cc:661-664,712)
+    b200_slice stack[64];
+    std::vector<b200_slice> heap;
+    b200_slice* flat = stack;
+    if (n > 64) {
+      heap.resize(n);
+      flat = heap.data();
+    }
+    for (size_t i = 0; i < n; i++) flat[i] = {GRPC_SLICE_START_PTR(slices[i]), GRPC_SLICE_LENGTH(slices[i])};
+    return b200_pair_send(p_, flat, n, byte_idx);
   }
   uint64_t Recv(void* buf, uint64_t cap) { return b200_pair_recv(p_, buf, cap); }   // pair.cc:264
   bool HasMessage() const { return b200_pair_has_message(p_) != 0; }                // pair.cc:288
