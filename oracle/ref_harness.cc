@@ -76,6 +76,12 @@ int ref_pair_connect(void* a, void* b) {
   t.join();
   return ok_a && ok_b;
 }
+// one side of Connect(): blocks until the peer's memory-region blob arrives, like the real thing
+int ref_pair_connect_to(void* p, const void* addr, size_t n) {
+  std::vector<char> v(static_cast<const char*>(addr), static_cast<const char*>(addr) + n);
+  return static_cast<PairPollable*>(p)->Connect(v) ? 1 : 0;
+}
+const char* ref_pair_error(void* p) { return static_cast<PairPollable*>(p)->get_error().c_str(); }
 size_t ref_pair_address(void* p, void* out, size_t cap) {
   auto b = static_cast<PairPollable*>(p)->get_self_address().bytes();
   if (cap >= b.size()) memcpy(out, b.data(), b.size());
