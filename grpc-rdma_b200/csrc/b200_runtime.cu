@@ -961,15 +961,20 @@ extern "C" void b200_service_stop(void) {
   }
   delete[] r.svc_w;
   r.svc_w = nullptr;
+  {
+    // the host poller thread reads the ready ring under scan_mu: hand it a null pointer before the free
+    std::lock_guard<std::mutex> lk(r.scan_mu);
+    ReadyEntry* ring = r.svc_ready;
+    r.svc_ready = nullptr;
+    cudaFreeHost(ring);
+  }
   cudaFreeHost(r.svc_cmds);
   cudaFreeHost(r.svc_done);
-  cudaFreeHost(r.svc_ready);
   cudaFreeHost(r.svc_host_scans);
   cudaFree(r.d_svc_ps);
   cudaFree(r.d_svc_last_ev);
   r.svc_cmds = nullptr;
   r.svc_done = nullptr;
-  r.svc_ready = nullptr;
   r.svc_host_scans = nullptr;
   r.d_svc_ps = nullptr;
   r.d_svc_last_ev = nullptr;

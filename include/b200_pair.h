@@ -191,6 +191,7 @@ int b200_poller_scan(b200_pair* const* pairs, size_t n, uint32_t* events);
  * callers must use stream-level waits.
  */
 int b200_service_start(int workers);
+/* Call with no b200_pair_send / recv in flight (they would wait for a worker that has left). */
 void b200_service_stop(void);
 int b200_service_running(void); /* number of worker CTAs, 0 = not running */
 /* out[0] commands executed, [1] ready-ring entries consumed, [2] ready-ring overruns,
