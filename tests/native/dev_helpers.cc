@@ -1,0 +1,17 @@
+// dev_helpers.cc -- TEST INFRASTRUCTURE: the product's frame / credit arithmetic (the B200_HD inlines of
+// grpc-rdma_b200/csrc/b200_dev.cuh that the kernels and the host runtime share) compiled for the host, so the
+// CPU tests can compare it with the reference's own functions (ring_buffer.h:180-189, ring_buffer.cc:99-116).
+#include <stdint.h>
+
+#define __align__(n) __attribute__((aligned(n)))  // nvcc spelling, for the host compiler
+#include "../../grpc-rdma_b200/csrc/b200_dev.cuh"
+
+extern "C" {
+uint64_t dev_round_up8(uint64_t v) { return b200::round_up8(v); }
+uint64_t dev_encoded_size(uint64_t p) { return b200::encoded_size(p); }
+uint64_t dev_calc_writable(uint64_t s) { return b200::calc_writable(s); }
+uint64_t dev_free_size(uint64_t cap, uint64_t head, uint64_t tail) { return b200::free_size(cap, head, tail); }
+uint64_t dev_writable_size(uint64_t cap, uint64_t head, uint64_t tail) { return b200::writable_size(cap, head, tail); }
+uint64_t dev_sizeof_pairdev() { return sizeof(b200::PairDev); }
+uint64_t dev_sizeof_svccmd() { return sizeof(b200::SvcCmd); }
+}
