@@ -388,3 +388,127 @@ extern "C" int drv_echo(const b200_pair_ops* ops, int n_msgs, uint64_t max_len, 
   drop_fixture(&f);
   return rc;
 }
+
+// Many connections on ONE engine pair (client engine, server engine): what a server pollset sees --
+// `n_conns` fds in the busy-poll scan / epoll set, reads and writes of different connections
+// interleaving in one pollable (ev_epollex_rdma_bpev_linux.cc:1104-1145 caps a pass at MAX_EPOLL_EVENTS
+// = 100 synthesized events, so more than 100 ready connections need several passes).  Every client sends
+// `rounds` messages of a connection-specific size and checks each echo.
+extern "C" int drv_multi_echo(const b200_pair_ops* ops, int n_conns, int rounds, uint64_t max_len, uint64_t seed,
+                              int busy_us, int enable_poller, int threaded, uint64_t* stats_out) {
+  b200_engine* ce = b200_engine_create(ops, busy_us);
+  b200_engine* se = threaded ? b200_engine_create(ops, busy_us) : ce;
+  std::vector<b200_endpoint*> cep(n_conns), sep(n_conns);
+  for (int c = 0; c < n_conns; c++) {
+    int sv[2];
+    if (socketpair(AF_UNIX, SOCK_STREAM, 0, sv) != 0) FAIL();
+    std::thread t([&] { sep[c] = b200_endpoint_create(se, sv[1], "ipv4:server", enable_poller); });
+    cep[c] = b200_endpoint_create(ce, sv[0], "ipv4:client", enable_poller);
+    t.join();
+    if (!cep[c] || !sep[c]) FAIL();
+  }
+  std::vector<Stream> cli, srv;
+  for (int c = 0; c < n_conns; c++) {
+    cli.push_back(Stream{cep[c], ce});
+    srv.push_back(Stream{sep[c], se});
+  }
+  const auto deadline = Clock::now() + std::chrono::seconds(300);
+  std::atomic<int> srv_rc{0};
+  std::atomic<bool> stop{false};
+  // server: poll all connections; whenever one has a complete message, echo it
+  auto serve = [&](bool until_stop) -> int {
+    std::vector<int> served(n_conns, 0);
+    int total = 0;
+    while (total < n_conns * rounds) {
+      if (until_stop && stop.load()) break;
+      if (Clock::now() > deadline) return __LINE__;
+      bool progress = false;
+      for (int c = 0; c < n_conns; c++) {
+        Stream* s = &srv[c];
+        if (!s->err.empty()) return __LINE__;
+        if (s->write_busy) continue;
+        if (s->inbuf.size() >= 8) {
+          uint64_t len;
+          memcpy(&len, s->inbuf.data(), 8);
+          const uint64_t nfr = (len + 16383) / 16384;
+          if (s->inbuf.size() >= 8 + len + 9 * nfr) {
+            std::vector<uint8_t> m;
+            if (!st_recv(s, &m, deadline)) return __LINE__;
+            st_send(s, m);
+            served[c]++;
+            total++;
+            progress = true;
+            continue;
+          }
+        }
+        if (!s->reading) {
+          s->reading = true;
+          b200_endpoint_read(s->ep, st_read_cb, s, 0);
+        }
+      }
+      if (!progress) b200_engine_work(se, 2);
+      if (!threaded) return 0;  // single-threaded mode: one sweep per call
+    }
+    while (threaded) {  // flush the last replies
+      bool busy = false;
+      for (auto& s : srv) busy = busy || s.write_busy;
+      if (!busy || Clock::now() > deadline) break;
+      b200_engine_work(se, 2);
+    }
+    return 0;
+  };
+  std::thread server;
+  if (threaded) server = std::thread([&] { srv_rc = serve(false); });
+  int rc = 0;
+  uint64_t st = seed ? seed : 1;
+  std::vector<std::vector<uint8_t>> sent(n_conns);
+  for (int r = 0; r < rounds && !rc; r++) {
+    for (int c = 0; c < n_conns; c++) {  // all connections have a request in flight at once
+      const uint64_t len = 1 + (xorshift(&st) % max_len);
+      sent[c].resize(len);
+      for (uint64_t j = 0; j < len; j += 8) {
+        uint64_t v = xorshift(&st);
+        memcpy(sent[c].data() + j, &v, std::min<uint64_t>(8, len - j));
+      }
+      while (cli[c].write_busy && Clock::now() < deadline) b200_engine_work(ce, 1);
+      st_send(&cli[c], sent[c]);
+    }
+    for (int c = 0; c < n_conns && !rc; c++) {
+      std::vector<uint8_t> reply;
+      if (threaded) {
+        if (!st_recv(&cli[c], &reply, deadline)) rc = __LINE__;
+      } else {
+        // one thread: alternate server sweeps and client progress until this reply is complete
+        while (!rc) {
+          int s_rc = serve(false);
+          if (s_rc) rc = s_rc;
+          Stream* s = &cli[c];
+          if (s->inbuf.size() >= 8) {
+            uint64_t len;
+            memcpy(&len, s->inbuf.data(), 8);
+            if (s->inbuf.size() >= 8 + len + 9 * ((len + 16383) / 16384) && !s->write_busy) break;
+          }
+          if (!s->reading && s->err.empty()) {
+            s->reading = true;
+            b200_endpoint_read(s->ep, st_read_cb, s, 0);
+          }
+          b200_engine_work(ce, 1);
+          if (Clock::now() > deadline || !s->err.empty()) rc = __LINE__;
+        }
+        if (!rc && !st_recv(&cli[c], &reply, deadline)) rc = __LINE__;
+      }
+      if (!rc && reply != sent[c]) rc = __LINE__;
+    }
+  }
+  stop = true;
+  if (threaded) server.join();
+  if (!rc && srv_rc) rc = srv_rc;
+  if (stats_out) b200_engine_stats(se, stats_out);
+  for (int c = 0; c < n_conns; c++) {
+    b200_endpoint_destroy(cep[c]);
+    b200_endpoint_destroy(sep[c]);
+  }
+  if (se != ce) b200_engine_destroy(se);
+  b200_engine_destroy(ce);
+  return rc;
+}

@@ -86,3 +86,13 @@ def test_echo_random_messages(drv):
     # thread-safe), sizes scaled to the small ring
     assert D.drv_echo(ops, 40, 300_000, 12345, 50, 0, 0, C.byref(nbytes)) == 0
     assert nbytes.value > 0
+
+
+def test_many_connections_on_one_engine(drv):
+    """120 connections in one pollable: more ready fds than one pass may synthesize events for
+    (MAX_EPOLL_EVENTS = 100), requests of all connections in flight at once, echoes checked."""
+    D, O, ops = drv
+    O.oracle_ops_config(16384, 30)
+    st = (C.c_uint64 * 4)()
+    assert D.drv_multi_echo(ops, 120, 3, 20_000, 99, 50, 0, 0, st) == 0
+    assert st[2] >= 120 * 3          # events synthesized by the busy-poll scan

@@ -69,3 +69,12 @@ def test_echo_two_threads(drv, busy_us, poller):
     nbytes = C.c_uint64(0)
     assert D.drv_echo(ops, 16, 3_000_000, 4711 + busy_us, busy_us, poller, 1, C.byref(nbytes)) == 0
     assert nbytes.value > 0
+
+
+@pytest.mark.parametrize("busy_us,poller", [(100, 0), (0, 1)])
+def test_many_connections_two_threads(drv, busy_us, poller):
+    """10 connections per engine, client and server engines on their own threads, all requests in flight at
+    once; with busy_us = 0 every wake-up comes from the reference Poller's eventfd kicks through epoll_wait."""
+    D, R, ops = drv
+    R.ref_ops_config(64)
+    assert D.drv_multi_echo(ops, 10, 3, 150_000, 7 + busy_us, busy_us, poller, 1, None) == 0
