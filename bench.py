@@ -129,6 +129,22 @@ def cpu_engine():
     return orlib.Oracle(), "port"
 
 
+def usable_cpus():
+    """Host threads this process may really use: the affinity mask, capped by a cgroup CPU quota if there is one
+    (os.cpu_count() reports the machine, not the container)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_sample(eng, lens, conns, ring_bytes, threads, msgs, warm=1):
     t, delivered, _ = eng.bench_stream(conns, threads, warm, msgs, ring_bytes, lens)
     return t, delivered
@@ -151,7 +167,7 @@ def cpu_conns_that_fit(conns, ring_bytes, msg_total, kind):
 
 def run_cpu_baseline(args, lens, payload_per_msg, seconds):
     eng, kind = cpu_engine()
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     ring = args.ring_kb * 1024
     conns = cpu_conns_that_fit(args.conns, ring, sum(lens), kind)
     threads = min(cores, conns)
@@ -175,7 +191,7 @@ def reference_arm(args):
     pkg = ge.load_package()
     lens = pkg.chttp2_slice_lens(args.msg_bytes)
     eng, kind = cpu_engine()
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     ring = args.ring_kb * 1024
     conns = cpu_conns_that_fit(args.conns, ring, sum(lens), kind)
     threads = min(cores, conns)
