@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-unary", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--msgs-per-step", type=int, default=1, help="experiment: messages per connection per step")
     ap.add_argument("--unary-bytes", type=int, default=1024)
     ap.add_argument("--unary-iters", type=int, default=2000)
@@ -218,6 +219,53 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------ NUMA
+
+def _parse_cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(local):
+    """Pin this rank (and every thread / pinned allocation it makes from now on: first touch) to the NUMA node
+    its GPU hangs off.  SCALE_r01: GPUs 0-3 sit on node 0, 4-7 on node 1; unbound ranks put their pinned
+    buffers wherever the launcher ran and half of the DMA traffic crossed the socket interconnect."""
+    info = {"bound": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        try:
+            bdf = subprocess.check_output(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id",
+                                           "--format=csv,noheader"], text=True).strip().lower()
+            bdf = bdf[-12:]  # nvidia-smi prints an 8-digit domain
+        except Exception as exc:
+            info["why"] = repr(exc)
+            return info
+    info["pci"] = bdf
+    try:
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            info["why"] = "no NUMA affinity reported"
+            return info
+        cpus = _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            info["why"] = "node cpus outside the affinity mask"
+            return info
+        os.sched_setaffinity(0, allowed)
+        info.update(bound=True, node=node, cpus=len(allowed))
+    except Exception as exc:
+        info["why"] = repr(exc)
+    return info
+
+
 # --------------------------------------------------------------------------- B200 arm
 
 def main():
@@ -234,6 +282,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    numa = bind_to_gpu_numa(local) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -257,6 +306,9 @@ def main():
     row = (((i * 2654435761) >> 11) & 255).to(torch.uint8)                       # b[i]
     offs = ((torch.arange(conns, device=dev, dtype=torch.int64) + rank * conns) * 131 & 255).to(torch.uint8)
     src = (row[None, :] + offs[:, None]).reshape(-1)                             # + 131*c (mod 256), one kernel
+    # a second, different payload: steps alternate between the two sources, so a step that delivered nothing
+    # would leave the previous step's (different) bytes in dst and the comparison after the loop would fail
+    src2 = src ^ 0x5A
     del i, row, offs
     dst = torch.zeros(conns * total, dtype=torch.uint8, device=dev)
 
@@ -276,6 +328,9 @@ def main():
         return pkg.Batch("send", sops, fl), pkg.Batch("recv", rops, fl), keep
 
     bs, br, keep = build_batches(src.data_ptr(), dst.data_ptr())
+    bs2, br2, keep_b = build_batches(src2.data_ptr(), dst.data_ptr())
+    br2.destroy()                      # same destinations: one recv batch serves both sources
+    sends, srcs = (bs, bs2), (src, src2)
     if args.stagger:
         # connections of a real server are at uncorrelated ring positions; without this every ring of the
         # job would sit at the same offset of its 16 MiB-aligned buffer on every step.  One preamble
@@ -300,9 +355,12 @@ def main():
     sh = C.c_void_p(stream.cuda_stream)
     assert sh.value, "need a non-default stream handle"
 
+    nstep = [0]
+
     def step():
-        bs.launch(sh)
+        sends[nstep[0] & 1].launch(sh)
         br.launch(sh)
+        nstep[0] += 1
 
     def barrier():
         if world > 1:
@@ -314,8 +372,9 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    assert bs.results(sh) == [total] * conns and br.results(sh) == [total] * conns, "warm-up step incomplete"
-    assert torch.equal(src, dst), "delivered bytes differ from what was sent"
+    last = sends[(nstep[0] - 1) & 1]
+    assert last.results(sh) == [total] * conns and br.results(sh) == [total] * conns, "warm-up step incomplete"
+    assert torch.equal(srcs[(nstep[0] - 1) & 1], dst), "delivered bytes differ from what was sent"
 
     # ---- timed region: device resident
     K = args.steps
@@ -326,10 +385,11 @@ def main():
     t_region0 = time.time()
     for k in range(K):
         ev[k][0].record(stream)
-        bs.launch(sh)
+        sends[nstep[0] & 1].launch(sh)
         ev[k][1].record(stream)
         br.launch(sh)
         ev[k][2].record(stream)
+        nstep[0] += 1
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     t_region1 = time.time()
@@ -338,8 +398,10 @@ def main():
     t_dev_ms = ev[0][0].elapsed_time(ev[K - 1][2])
     send_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
     recv_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
-    assert bs.results(sh) == [total] * conns and br.results(sh) == [total] * conns
-    assert torch.equal(src, dst)
+    last = sends[(nstep[0] - 1) & 1]
+    assert last.results(sh) == [total] * conns and br.results(sh) == [total] * conns
+    # the LAST timed step's payload (the step before it carried the other one)
+    assert torch.equal(srcs[(nstep[0] - 1) & 1], dst), "last timed step did not deliver its bytes"
     if world > 1:
         t = torch.tensor([t_dev_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -384,7 +446,7 @@ def main():
 
     unary = None
     if rank == 0 and not args.no_unary:
-        for b in (bs, br):
+        for b in (bs, bs2, br):
             b.destroy()
         try:
             unary = run_unary(args, pkg, L, with_cpu=(world == 1 and not args.no_cpu_baseline))
@@ -426,6 +488,7 @@ def main():
             "unary": unary,
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "numa": numa,
             "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)
@@ -499,16 +562,20 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
     # one pinned slice per connection, 256-byte aligned like every b200_mem_alloc_host block.
     dstride = (total + 255) // 256 * 256
     hsrc = L.b200_mem_alloc_host(nbytes)
+    hsrc2 = L.b200_mem_alloc_host(nbytes)
     hdst = L.b200_mem_alloc_host(conns * dstride)
-    if not hsrc or not hdst:
+    if not hsrc or not hsrc2 or not hdst:
         return {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "pinned allocation failed: " + pkg.last_error()}
     import numpy as np
     hs = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(hsrc))
+    hs2 = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(hsrc2))
     hd = np.ctypeslib.as_array((C.c_uint8 * (conns * dstride)).from_address(hdst)).reshape(conns, dstride)
     i = np.arange(total, dtype=np.uint64)
     for c in range(conns):
         hs[c * total:(c + 1) * total] = ((i * np.uint64(40503) >> np.uint64(5)) + np.uint64(17 * c)).astype(np.uint8)
+    np.bitwise_xor(hs, 0xA5, out=hs2)      # steps alternate between two different payloads (see main())
+    hsv = (hs.reshape(conns, total), hs2.reshape(conns, total))
     K = args.e2e_steps or min(args.steps, 8)
     results = {}
     modes = ["zerocopy", "staged"] if args.e2e_mode == "auto" else [args.e2e_mode]
@@ -516,22 +583,26 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
         if mode == "zerocopy":
             # kernels address the pinned host slices / destinations directly: bytes cross PCIe once each way
             bs, br, keep = build_batches(hsrc, hdst, pkg.ZEROCOPY, dstride)
-
-            def step():
-                bs.launch(sh)
-                br.launch(sh)
+            bs2, br2, keep2 = build_batches(hsrc2, hdst, pkg.ZEROCOPY, dstride)
+            lane_stream = sh
         else:
             # the library's host-staged path: per lane H2D -> k_send ... k_recv -> D2H on internal streams
             bs, br, keep = build_batches(hsrc, hdst, 0, dstride)
+            bs2, br2, keep2 = build_batches(hsrc2, hdst, 0, dstride)
+            lane_stream = None
+        br2.destroy()
+        sends = (bs, bs2)
+        n = [0]
 
-            def step():
-                bs.launch(None)
-                br.launch(None)
+        def step():
+            sends[n[0] & 1].launch(lane_stream)
+            br.launch(lane_stream)
+            n[0] += 1
         hd[:] = 0
         step()
         L.b200_lanes_join(None)
         torch.cuda.synchronize()
-        ok = bool(np.array_equal(hs.reshape(conns, total), hd[:, :total]))
+        ok = bool(np.array_equal(hsv[0], hd[:, :total]))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if dist is not None:
             dist.barrier()
@@ -550,12 +621,16 @@ def run_e2e(args, pkg, L, pairs, lens, total, conns, msg, world, dist, dev, stre
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        ok = ok and bs.results(sh) == [total] * conns and br.results(sh) == [total] * conns
+        # after the timed loop: the host destination must hold the LAST step's payload, bit for bit
+        ok = ok and bool(np.array_equal(hsv[(n[0] - 1) & 1], hd[:, :total]))
+        ok = ok and sends[(n[0] - 1) & 1].results(sh) == [total] * conns and br.results(sh) == [total] * conns
         results[mode] = {"GBps": world * conns * K * msg / (ms * 1e-3) / 1e9, "ms_per_step": ms / K, "intact": ok,
                          "_wall": (tw0, tw1)}
         bs.destroy()
+        bs2.destroy()
         br.destroy()
     L.b200_mem_free_host(hsrc)
+    L.b200_mem_free_host(hsrc2)
     L.b200_mem_free_host(hdst)
     best = max((m for m in results if results[m]["intact"]), key=lambda m: results[m]["GBps"], default=None)
     if best is None:
