@@ -101,6 +101,7 @@ _SIGS = {
     "b200_service_stop": (None, []),
     "b200_service_running": (C.c_int, []),
     "b200_service_stats": (None, [C.POINTER(C.c_uint64)]),
+    "b200_service_eager_hits": (C.c_uint64, []),
     "b200_pairs_send": (C.c_int, [C.POINTER(SendOp), C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]),
     "b200_pairs_recv": (C.c_int, [C.POINTER(RecvOp), C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]),
     "b200_batch_prepare_send": (C.c_void_p, [C.POINTER(SendOp), C.c_size_t, C.c_int]),

@@ -96,6 +96,8 @@ struct SendOpDev {
   const SliceDev* slices;
   uint64_t nslices;
   uint64_t byte_idx;
+  uint64_t nreal;  // slices [nreal, nslices) only count towards total_slice_size (pair.cc:661-664): the host folds
+                   // what lies beyond max_sge into one trailing pseudo-slice that must never be dereferenced
 };
 
 struct RecvOpDev {
@@ -120,30 +122,80 @@ constexpr uint32_t kStConnected = 2;
 constexpr uint32_t kStHalfClosed = 3;
 constexpr uint32_t kStError = 5;
 
-// ---- persistent service kernel (k_service): host -> device commands in pinned mapped memory.
-// One command slot per worker CTA; the host writes the fields, then bumps `seq` (release); the
-// CTA polls `seq` (acquire, system scope), runs the op with the same code as k_send / k_recv and
-// answers in SvcDone.  The last CTA of the grid is the poller: it scans the connection table
-// continuously, keeps the host-visible mirrors current and appends readiness CHANGES to the
-// ready ring (warp-aggregated: one atomic per warp).
-constexpr uint32_t kSvcSend = 1, kSvcRecv = 2, kSvcStop = 3;
-constexpr uint32_t kSvcInline = 5;  // slices carried inside the command (a unary call has 2-4)
+// ---- persistent service (b200_service_*): three resident kernels.
+//   owners  (k_svc_owner): one WARP per command queue.  The host posts 128-byte commands into the
+//           queue's ring in pinned mapped memory; the warp polls it (two entries per trip over PCIe),
+//           executes small Send / Recv calls entirely by itself -- plan, copy, cursors, credit,
+//           mirrors: no CTA barrier, no lock (both ends of a loopback connection map to the same
+//           owner, so everything that touches a connection's small ops is program-ordered) -- and
+//           hands anything larger to the pool through a mailbox in device memory.
+//   pool    (k_svc_big): CTAs that run send_body / recv_body (the k_send / k_recv code) on mailbox
+//           jobs and answer the host themselves.
+//   poller  (k_svc_poll): the resident readiness scan of the BPEV design (ready ring).
+constexpr uint32_t kSvcSend = 1, kSvcRecv = 2, kSvcStop = 3, kSvcRetire = 4, kSvcNop = 5;
+constexpr uint32_t kSvcInline = 5;     // slices carried inside the command (a unary call has 2-4)
+constexpr uint32_t kOwnQ = 16;         // command entries per owner queue
+constexpr uint32_t kOwnBoxes = 8;      // pool jobs in flight per owner
+constexpr uint32_t kSmallMax = 8192;   // bytes one warp moves by itself; larger ops go to the pool
+constexpr uint32_t kEagerMax = 2048;   // frames up to this size are pushed to the receiver's host slot
+constexpr uint32_t kSvcSliceArea = 1024;  // pinned slice descriptors per command entry
 struct __align__(128) SvcCmd {
-  uint32_t seq;      // command number, written last by the host
-  uint32_t op;       // kSvcSend / kSvcRecv / kSvcStop
+  uint32_t stamp;    // ticket + 1, written last by the host (first 64-byte half of the line)
+  uint32_t op;       // kSvc*
   int32_t slot;
   uint32_t flags;    // B200_BATCH_*
   uint64_t ptr;      // send: SliceDev* (GPU-addressable; unused when n <= kSvcInline)   recv: destination
-  uint64_t n;        // send: nslices                        recv: capacity
+  uint64_t n;        // send: nslices                        recv / retire: capacity
   uint64_t byte_idx;
   SliceDev inl[kSvcInline];  // send: the slice list itself when it is short -- no second trip over PCIe
+  uint32_t nreal;    // send: slices [nreal, n) only count towards total_slice_size (never dereferenced)
+  uint32_t stamp2;   // = stamp, in the second 64-byte half: the two halves may be read by separate PCIe reads
 };
 static_assert(sizeof(SvcCmd) == 128, "one command = one 128-byte line");
-struct __align__(32) SvcDone {
-  uint64_t bytes, calls;
-  uint32_t seq;      // = SvcCmd.seq once the op is finished and its bytes are visible
-  uint32_t _pad[3];
+struct __align__(16) SvcDone {  // one 16-byte store: the fields become visible together
+  uint64_t bytes;
+  uint32_t calls;
+  uint32_t seq;      // = SvcCmd.stamp once the op is finished and its bytes are visible
 };
+static_assert(sizeof(SvcDone) == 16, "one answer = one 16-byte store");
+// service-only device state of a pair
+struct PairSvc {
+  uint64_t delivered;  // payload bytes this pair's Recv calls have returned since the service started
+  uint64_t pushed_at;  // value of `delivered` for which the frame at the head was pushed to the host slot (~0: none)
+};
+// host-visible record of an eagerly pushed frame (pinned): the frame at the head of the ring, complete and
+// <= kEagerMax bytes, copied to the pair's host slot so that Recv does not need a trip to the GPU.  No
+// ordering between the payload stores and the record is assumed: `csum` covers payload, size and `at`.
+struct __align__(32) EagerRec {
+  uint64_t at;     // = PairSvc.delivered when the frame was pushed: valid only while the host's count agrees
+  uint64_t csum;
+  uint32_t size;
+  uint32_t magic;
+  uint64_t _pad;
+};
+constexpr uint32_t kEagerMagic = 0xEA6E7001u;
+// mailbox owner -> pool (device memory)
+struct __align__(128) BigBox {
+  uint32_t state;    // 0 free, 1 posted, 2 running, 3 done (owner reaps)
+  uint32_t kind;     // kSvcSend / kSvcRecv
+  int32_t slot;
+  uint32_t flags;
+  uint64_t ptr, n, byte_idx, nreal;
+  SliceDev inl[kSvcInline];
+  SvcDone* done;     // host entry the pool answers into
+  uint32_t seq;
+  uint32_t _pad;
+  OpResult res;
+};
+B200_HD uint64_t eager_mix(uint64_t x) {
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 32;
+  return x;
+}
+// checksum contribution of payload word j (tail bytes beyond `size` zeroed); XOR of all + eager_mix(at * 31 + size)
+B200_HD uint64_t eager_word(uint64_t w, uint32_t j) { return eager_mix(w + (uint64_t)(j + 1) * 0x9E3779B97F4A7C15ull); }
+
 constexpr uint32_t kReadyRing = 4096;  // entries; entry i of the stream sits at i % kReadyRing
 struct ReadyEntry {                    // one 8-byte store
   uint32_t stamp;                      // stream index + 1 (0 = never written)
@@ -156,6 +208,20 @@ struct SvcPollState {                  // device memory
   uint32_t ready_next;                 // next stream index of the ready ring
   uint32_t scans;                      // completed scans (liveness)
 };
+struct SvcParams {
+  PairDev* pairs;
+  PairSvc* psvc;
+  SvcCmd* cmds;        // [nowners][kOwnQ], pinned
+  SvcDone* done;       // [nowners][kOwnQ], pinned
+  BigBox* boxes;       // [nowners][kOwnBoxes], device
+  EagerRec* erec;      // [kMaxPairs], pinned
+  uint8_t* eslots;     // [kMaxPairs][kEagerMax], pinned
+  SvcPollState* ps;
+  uint32_t* last_ev;
+  ReadyEntry* ready;
+  uint32_t* host_scans;
+  int nowners, nbig;
+};
 
 // launch wrappers (b200_kernels.cu)
 void launch_send(PairDev* pairs, const SendOpDev* ops, OpResult* results, int nops, void* stream);
@@ -163,8 +229,8 @@ void launch_recv(PairDev* pairs, const RecvOpDev* ops, OpResult* results, int no
 void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, uint32_t* ready_count,
                       int32_t* ready_slots, int n, void* stream);
 
-void launch_service(PairDev* pairs, SvcCmd* cmds, SvcDone* done, SvcPollState* ps, uint32_t* last_ev,
-                    ReadyEntry* ready, uint32_t* host_scans, int nworkers, void* stream);
+// owners / pool / poller on three streams; returns false when the resident grids cannot be co-resident
+bool launch_service(const SvcParams& sp, void* s_owner, void* s_big, void* s_poll);
 
 void launch_probe_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,
                        int threads, uint32_t mis, uint32_t item_bytes, uint32_t dynamic, void* stream);

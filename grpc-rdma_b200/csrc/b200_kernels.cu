@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "b200_dev.cuh"
 
 #ifndef B200_RECV_PROXY_FENCE
@@ -33,6 +35,10 @@
 namespace b200 {
 
 // ------------------------------------------------------------ memory helpers
+
+// Resident kernels touch a pair's line from whichever SM serves the op, so nothing of it may come out of a
+// stale L1 line: read through (volatile) every time.
+#define VL(x) (*(volatile decltype(x)*)&(x))
 
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   uint4 r;
@@ -409,7 +415,7 @@ __device__ __noinline__ void send_produce_segment(const SendOpDev& op, const Pai
     }
     const uint64_t cur = S.cur, bidx = S.bidx;
     const uint64_t idx = cur + lane;
-    const bool valid = lane < S.max_sge && idx < op.nslices;
+    const bool valid = lane < S.max_sge && idx < op.nreal;  // never past the slices that may be dereferenced
     const uint8_t* ptr = nullptr;
     uint64_t len = 0;
     if (valid) {
@@ -582,16 +588,16 @@ __device__ __forceinline__ void send_body(PairDev* __restrict__ pairs, const Sen
   if (tid < kQI) q[tid].ready = 0;
   if (tid == 0) {
     s_total = 0;
-    s_status = P->status;
-    PS.rt = P->remote_tail;
-    PS.cap = P->cap;
-    PS.staging = P->cap / 2;  // send_buf_size = recv_buf_size / 2, pair.cc:104
-    PS.max_sge = P->max_sge;
+    s_status = *(volatile uint32_t*)&P->status;
+    PS.rt = *(volatile uint64_t*)&P->remote_tail;
+    PS.cap = *(volatile uint64_t*)&P->cap;
+    PS.staging = PS.cap / 2;  // send_buf_size = recv_buf_size / 2, pair.cc:104
+    PS.max_sge = *(volatile uint32_t*)&P->max_sge;
     PS.cur = 0;
     PS.bidx = op.byte_idx;
     PS.written_total = 0;
     PS.ncalls = 0;
-    PS.partial = P->partial_write;
+    PS.partial = *(volatile uint32_t*)&P->partial_write;
     PS.last_rh = ~0ull;  // not a ring offset: the first call always fences
   }
   __syncthreads();
@@ -610,9 +616,9 @@ __device__ __forceinline__ void send_body(PairDev* __restrict__ pairs, const Sen
     return;
   }
   if (tid == 0) PS.total_left = s_total - op.byte_idx;
-  const uint64_t cap = P->cap, mask = cap - 1;
-  uint8_t* ring = P->peer_ring;
-  const bool sys_scope = P->wire != 0;
+  const uint64_t cap = VL(P->cap), mask = cap - 1;
+  uint8_t* ring = VL(P->peer_ring);
+  const bool sys_scope = VL(P->wire) != 0;
 
   while (true) {
     if (tid == 0) {
@@ -648,17 +654,19 @@ __device__ __forceinline__ void send_body(PairDev* __restrict__ pairs, const Sen
     result->calls = PS.ncalls;
     const bool conc = (op.flags & kFlagConcurrent) != 0;
     mirror_lock(P, conc);
-    publish_mirror_tx(P->mirror, P);
+    publish_mirror_tx(VL(P->mirror), P);
     mirror_unlock(P, conc);
     // loopback wire: the peer lives in this table, refresh its readiness hint
-    if (P->peer_slot >= 0 && PS.written_total) {
-      PairDev* Q = &pairs[P->peer_slot];
-      if (Q->mirror) {
+    const int peer_slot = VL(P->peer_slot);
+    if (peer_slot >= 0 && PS.written_total) {
+      PairDev* Q = &pairs[peer_slot];
+      PairMirror* qm = VL(Q->mirror);
+      if (qm) {
         uint32_t hm;
         uint64_t rd;
         mirror_lock(Q, conc);
-        rx_probe<false>(Q->ring, Q->cap, *(volatile uint64_t*)&Q->head, *(volatile uint64_t*)&Q->remain, hm, rd);
-        volatile PairMirror* vm = Q->mirror;
+        rx_probe<false>(VL(Q->ring), VL(Q->cap), *(volatile uint64_t*)&Q->head, *(volatile uint64_t*)&Q->remain, hm, rd);
+        volatile PairMirror* vm = qm;
         vm->has_message = hm;
         vm->readable = rd;
         mirror_unlock(Q, conc);
@@ -1013,11 +1021,11 @@ __device__ __forceinline__ void recv_body(PairDev* __restrict__ pairs, const Rec
 
   if (tid < kQI) q[tid].ready = 0;
   if (tid == 0) {
-    s_status = P->status;
-    SS.head = P->head;
-    SS.mh = P->moving_head;
-    SS.remain = P->remain;
-    SS.acc = P->acc;
+    s_status = *(volatile uint32_t*)&P->status;
+    SS.head = *(volatile uint64_t*)&P->head;
+    SS.mh = *(volatile uint64_t*)&P->moving_head;
+    SS.remain = *(volatile uint64_t*)&P->remain;
+    SS.acc = *(volatile uint64_t*)&P->acc;
     SS.cap_left = op.cap;
     SS.delivered = 0;
     SS.ncalls = 0;
@@ -1031,8 +1039,8 @@ __device__ __forceinline__ void recv_body(PairDev* __restrict__ pairs, const Rec
     }
     return;
   }
-  uint8_t* ring = P->ring;
-  const uint64_t cap = P->cap, mask = cap - 1;
+  uint8_t* ring = VL(P->ring);
+  const uint64_t cap = VL(P->cap), mask = cap - 1;
 
   while (true) {
     if (tid == 0) {
@@ -1054,11 +1062,13 @@ __device__ __forceinline__ void recv_body(PairDev* __restrict__ pairs, const Rec
     const bool done = ctl.op_done != 0;
     if (tid == 0 && credit) {
       // updateStatus, pair.cc:624-641: 16-byte status_report to the peer
-      const bool conc = (op.flags & kFlagConcurrent) != 0 && P->peer_slot >= 0;
-      PairDev* Q = conc ? &pairs[P->peer_slot] : nullptr;
+      const int peer_slot = VL(P->peer_slot);
+      const bool conc = (op.flags & kFlagConcurrent) != 0 && peer_slot >= 0;
+      PairDev* Q = conc ? &pairs[peer_slot] : nullptr;
       if (conc) mirror_lock(Q, true);
-      st_release_v2u64(P->peer_credit, SS.credit_val, 0);
-      if (P->peer_mirror) ((volatile PairMirror*)P->peer_mirror)->credit_head = SS.credit_val;
+      st_release_v2u64(VL(P->peer_credit), SS.credit_val, 0);
+      PairMirror* pm = VL(P->peer_mirror);
+      if (pm) ((volatile PairMirror*)pm)->credit_head = SS.credit_val;
       if (conc) mirror_unlock(Q, true);
       SS.credit_flag = 0;
     }
@@ -1077,7 +1087,7 @@ __device__ __forceinline__ void recv_body(PairDev* __restrict__ pairs, const Rec
     const bool conc = (op.flags & kFlagConcurrent) != 0;
     mirror_lock(P, conc);
     rx_probe<false>(ring, cap, SS.head, SS.remain, hm, rd);
-    publish_mirror_rx(P->mirror, P, hm, rd);
+    publish_mirror_rx(VL(P->mirror), P, hm, rd);
     mirror_unlock(P, conc);
   }
 }
@@ -1119,8 +1129,13 @@ k_poll_scan(PairDev* __restrict__ pairs, const int32_t* __restrict__ slots, uint
         if (hm) ev |= kEvReadable;
         if (pw) ev |= kEvWritable;
       }
-      publish_mirror_rx(P->mirror, P, hm, rd);
-      publish_mirror_tx(P->mirror, P);
+      // On the loopback wire the kernels that land bytes / return credit refresh the mirrors themselves, in
+      // order with their own completion; a scan running beside them could only overwrite that with an older
+      // view (and b200_pair_recv / send answer "nothing to do" from the mirror without launching anything).
+      if (P->peer_slot < 0) {
+        publish_mirror_rx(P->mirror, P, hm, rd);
+        publish_mirror_tx(P->mirror, P);
+      }
     } else if (st == kStError || st == kStHalfClosed) {
       ev = kEvReadable;
     }
@@ -1137,12 +1152,595 @@ k_poll_scan(PairDev* __restrict__ pairs, const int32_t* __restrict__ slots, uint
 }
 
 // =========================================================================
-// k_service: persistent kernel.  Worker CTAs execute Send / Recv commands posted by the host into
-// pinned mapped memory with exactly the code of k_send / k_recv (no launch, no stream sync on the
-// unary path); the last CTA is the poller of the BPEV design (Poller::begin_polling,
-// poller.cc:52-106, and the engine's scan, ev_epollex_rdma_bpev_linux.cc:1104-1145) as a
-// resident scan loop.
+// Persistent service: k_svc_owner (one warp per host command queue), k_svc_big (pool CTAs running
+// send_body / recv_body on mailbox jobs), k_svc_poll (resident readiness scan).  See b200_dev.cuh.
 // =========================================================================
+
+__device__ __forceinline__ uint64_t ld_sys_u64(const void* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_sys_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_sys_v4(void* p, uint4 v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_sys_u64(void* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint8_t ld_volatile_u8(const void* p) { return *(const volatile uint8_t*)p; }
+
+// ---- warp-level byte movers of the small paths (no shared memory, no barrier) ----------------
+
+// n bytes from `src` (any alignment; device or pinned host memory: system-coherent loads that bypass
+// L1, the host reuses its buffers) into the ring at payload offset `off` (8-byte aligned; wraps at
+// cap).  Whole 8-byte words are written, the tail padded with zeros (pad bytes are never delivered).
+__device__ __forceinline__ void warp_copy_to_ring(uint8_t* ring, uint64_t mask, uint64_t off, const uint8_t* src,
+                                                  uint32_t n, uint32_t lane) {
+  const uintptr_t s = reinterpret_cast<uintptr_t>(src);
+  const uint32_t sb = (uint32_t)(s & 7), sh = sb * 8;
+  const uint64_t* s0 = reinterpret_cast<const uint64_t*>(s & ~(uintptr_t)7);
+  const uint32_t words = (n + 7) >> 3;
+  for (uint32_t base = 0; base < words; base += 32) {
+    const uint32_t j = base + lane;
+    const bool act = j < words;
+    uint64_t lo = 0, hi = 0;
+    if (act) lo = ld_sys_u64(s0 + j);
+    const uint64_t nxt = __shfl_down_sync(0xffffffffu, lo, 1);
+    uint64_t w = lo;
+    if (sh) {
+      // the last payload byte of word j is byte min(8 j + 8, n) - 1; it lives in aligned word (sb + b) / 8
+      const uint32_t lastb = (8 * j + 8 < n ? 8 * j + 8 : n) - 1;
+      const bool need_hi = act && (sb + lastb) / 8 > j;
+      if (need_hi) hi = (lane == 31 || j + 1 >= words) ? ld_sys_u64(s0 + j + 1) : nxt;
+      w = (lo >> sh) | (hi << (64 - sh));
+    }
+    if (act) {
+      const uint32_t rem = n - 8 * j;
+      if (rem < 8) w &= (1ull << (8 * rem)) - 1;
+      *reinterpret_cast<uint64_t*>(ring + ((off + 8ull * j) & mask)) = w;
+    }
+  }
+}
+
+// n ring bytes starting at offset `off` (any alignment, wraps) to `dst` (any alignment; device or
+// pinned host memory).  With `words_out` the 8-byte words that were stored at aligned positions
+// are also folded into an eager checksum (only used with off, dst 8-byte aligned).
+__device__ __forceinline__ void warp_copy_from_ring(uint8_t* dst, const uint8_t* ring, uint64_t mask, uint64_t off,
+                                                    uint32_t n, uint32_t lane) {
+  const uintptr_t d = reinterpret_cast<uintptr_t>(dst);
+  uint32_t head = (uint32_t)((8 - (d & 7)) & 7);
+  if (head > n) head = n;
+  if (lane < head) dst[lane] = ld_volatile_u8(ring + ((off + lane) & mask));
+  const uint32_t nwords = (n - head) >> 3;
+  const uint64_t o = off + head;
+  const uint32_t sh = (uint32_t)(o & 7) * 8;
+  const uint64_t o0 = o & ~7ull;
+  for (uint32_t k = lane; k < nwords; k += 32) {
+    const uint64_t lo = ld_volatile_u64(ring + ((o0 + 8ull * k) & mask));
+    uint64_t w = lo;
+    if (sh) {
+      const uint64_t hi = ld_volatile_u64(ring + ((o0 + 8ull * k + 8) & mask));
+      w = (lo >> sh) | (hi << (64 - sh));
+    }
+    *reinterpret_cast<uint64_t*>(dst + head + 8ull * k) = w;
+  }
+  const uint32_t tail = n - head - 8 * nwords;
+  if (lane < tail) dst[head + 8 * nwords + lane] = ld_volatile_u8(ring + ((o + 8ull * nwords + lane) & mask));
+}
+
+// zero [zs, zs + zl) of the ring (any alignment, wraps)
+__device__ __forceinline__ void warp_zero_ring(uint8_t* ring, uint64_t mask, uint64_t zs, uint64_t zl, uint32_t lane) {
+  uint64_t head = (8 - (zs & 7)) & 7;
+  if (head > zl) head = zl;
+  if (lane < head) ring[(zs + lane) & mask] = 0;
+  const uint64_t nwords = (zl - head) >> 3;
+  const uint64_t o = zs + head;
+  for (uint64_t k = lane; k < nwords; k += 32) *reinterpret_cast<uint64_t*>(ring + ((o + 8 * k) & mask)) = 0;
+  const uint64_t tail = zl - head - 8 * nwords;
+  if (lane < tail) ring[(o + 8 * nwords + lane) & mask] = 0;
+}
+
+// ---- readiness of pair Q after something changed in its ring / cursors: mirror + eager push -----
+// Called by the owner warp only (Q's small Recv / Retire, or the small Send of Q's loopback peer:
+// all program-ordered in this warp).  The frame at the head, when complete and <= kEagerMax, is
+// copied to Q's host slot first, then the mirror says "has message": a Recv that finds a valid
+// record takes the bytes from the slot and posts an asynchronous Retire instead of waiting for a
+// trip to the GPU and back.
+__device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, PairDev* Q, int qslot, bool full_mirror,
+                                               uint32_t lane) {
+  const uint64_t cap = VL(Q->cap), mask = cap - 1;
+  const uint8_t* ring = VL(Q->ring);
+  const uint64_t head = VL(Q->head), remain = VL(Q->remain);
+  PairMirror* mirror = VL(Q->mirror);
+  uint32_t hm = 0;
+  uint64_t rd = 0;
+  if (remain > 0) {
+    hm = 1;
+    rd = remain;
+  } else {
+    const uint64_t hdr = ld_volatile_u64(ring + head);
+    hm = hdr != 0;
+    if (hdr != 0 && hdr <= cap - kReserved) {
+      const uint64_t foot = ld_volatile_u64(ring + ((head + 8 + round_up8(hdr)) & mask));
+      if (foot == kFooter) rd = hdr;
+    }
+    PairSvc* S = &sp.psvc[qslot];
+    if (rd != 0 && rd <= kEagerMax && sp.erec != nullptr) {
+      const uint64_t at = VL(S->delivered);
+      if (VL(S->pushed_at) != at) {
+        uint8_t* slot = sp.eslots + (size_t)qslot * kEagerMax;
+        const uint32_t words = (uint32_t)((rd + 7) >> 3);
+        uint64_t cs = 0;
+        for (uint32_t j = lane; j < words; j += 32) {
+          uint64_t w = ld_volatile_u64(ring + ((head + 8 + 8ull * j) & mask));
+          const uint32_t rem = (uint32_t)rd - 8 * j;
+          if (rem < 8) w &= (1ull << (8 * rem)) - 1;
+          st_sys_u64(slot + 8ull * j, w);
+          cs ^= eager_word(w, j);
+        }
+        for (int o = 16; o > 0; o >>= 1) cs ^= __shfl_xor_sync(0xffffffffu, cs, o);
+        cs ^= eager_mix(at * 31 + rd);
+        if (lane == 0) {
+          EagerRec* r = &sp.erec[qslot];
+          uint4 a, b;
+          a.x = (uint32_t)at; a.y = (uint32_t)(at >> 32); a.z = (uint32_t)cs; a.w = (uint32_t)(cs >> 32);
+          b.x = (uint32_t)rd; b.y = kEagerMagic; b.z = 0; b.w = 0;
+          st_sys_v4(r, a);
+          st_sys_v4(reinterpret_cast<uint8_t*>(r) + 16, b);
+          S->pushed_at = at;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0 && mirror) {
+    volatile PairMirror* vm = mirror;
+    if (full_mirror) {
+      vm->head = head;
+      vm->moving_head = VL(Q->moving_head);
+      vm->remain = remain;
+      vm->acc = VL(Q->acc);
+    }
+    vm->readable = rd;
+    vm->has_message = hm;
+  }
+}
+
+// ---- one PairPollable::Send call by one warp (pair.cc:645-734): <= kSvcInline slices, <= kSmallMax bytes.
+// Same planning arithmetic as send_produce_segment (credit snapshot once, prefix scan of encoded sizes,
+// first slice that does not fit is cut to CWS(room), zero-length slice stops the call), then the warp
+// moves the frames itself.
+__device__ __forceinline__ void svc_send_small(const SvcParams& sp, const SvcCmd& c, OpResult& res, uint32_t lane) {
+  PairDev* P = &sp.pairs[c.slot];
+  res.bytes = 0;
+  res.calls = 0;
+  if (VL(P->status) != kStConnected) return;  // pair.cc:657
+  const uint64_t cap = VL(P->cap), mask = cap - 1;
+  uint8_t* ring = VL(P->peer_ring);
+  const bool sys_scope = VL(P->wire) != 0;
+  const uint64_t rt = VL(P->remote_tail);
+  const uint32_t max_sge = VL(P->max_sge);
+  const int peer_slot = VL(P->peer_slot);
+  PairMirror* mirror = VL(P->mirror);
+  const uint64_t rh = sys_scope ? ld_acquire_u64(&P->credit_head) : ld_volatile_u64(&P->credit_head);
+  const uint64_t staging = cap / 2;
+  const uint32_t nsl = (uint32_t)c.n;
+  const uint32_t look = (uint32_t)(c.nreal < max_sge ? c.nreal : max_sge);
+  const uint8_t* ptr = nullptr;
+  uint64_t len = 0, raw = 0;
+  if (lane < nsl) {
+    raw = c.inl[lane].len;
+    if (lane < look) {
+      const uint64_t skip = lane == 0 ? c.byte_idx : 0;
+      ptr = c.inl[lane].ptr + skip;
+      len = raw - skip;
+    }
+  }
+  const bool valid = lane < look;
+  uint64_t total = raw;  // total_slice_size, pair.cc:661-664
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  total -= c.byte_idx;
+  const uint64_t e = valid ? encoded_size(len) : 0;
+  uint64_t incl = e;
+  for (int o = 1; o < 8; o <<= 1) {  // kSvcInline <= 8 lanes carry slices
+    uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  const uint64_t a = incl - e;
+  const uint64_t fr = free_size(cap, rh, rt);
+  const uint64_t lim = staging < fr ? staging : fr;
+  const uint64_t room = calc_writable(lim > a ? lim - a : 0);
+  const bool fits = valid && len != 0 && len <= room;
+  const unsigned bad = __ballot_sync(0xffffffffu, !fits);
+  const int nfull = __ffs(bad) - 1;  // lanes >= look are "bad": nfull <= look
+  uint64_t p = 0;
+  if ((int)lane < nfull) p = len;
+  else if ((int)lane == nfull && valid && len != 0) p = room;  // cut: space ran out
+  const unsigned fmask = __ballot_sync(0xffffffffu, p != 0);
+  const uint32_t nframes = __popc(fmask);
+  uint64_t wsum = p, esum = p ? encoded_size(p) : 0;
+  for (int o = 16; o > 0; o >>= 1) {
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    esum += __shfl_xor_sync(0xffffffffu, esum, o);
+  }
+  const uint64_t foff = (rt + a) & mask;
+  for (uint32_t f = 0; f < nframes; f++) {
+    const uint8_t* fsrc = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(ptr), f));
+    const uint32_t fp = (uint32_t)__shfl_sync(0xffffffffu, p, f);
+    const uint64_t fo = __shfl_sync(0xffffffffu, foff, f);
+    if (lane == 0) *reinterpret_cast<uint64_t*>(ring + fo) = fp;  // AppendHeader
+    warp_copy_to_ring(ring, mask, (fo + 8) & mask, fsrc, fp, lane);
+  }
+  // footers last (ring_buffer.cc:75-96): everything else of the call is made visible first
+  if (sys_scope) __threadfence_system();
+  else __threadfence();
+  __syncwarp();
+  if (p != 0) *reinterpret_cast<uint64_t*>(ring + ((foff + 8 + round_up8(p)) & mask)) = kFooter;
+  __syncwarp();
+  if (lane == 0) {
+    P->remote_tail = (rt + esum) & mask;
+    P->partial_write = wsum < total;  // pair.cc:712
+    if (mirror) {
+      volatile PairMirror* vm = mirror;
+      vm->remote_tail = (rt + esum) & mask;
+      vm->partial_write = wsum < total;
+      vm->credit_head = rh;
+      vm->peer_exit = *(volatile const uint32_t*)&P->credit_exit;
+    }
+  }
+  res.bytes = wsum;
+  res.calls = wsum ? 1 : 0;
+  __syncwarp();
+  if (peer_slot >= 0 && wsum) {
+    __threadfence();  // the footers before the probe that reads them back
+    svc_rx_refresh(sp, &sp.pairs[peer_slot], peer_slot, false, lane);
+  }
+}
+
+// ---- one PairPollable::Recv call by one warp (ring_buffer.cc:122-191 + pair.cc:264-286).  Returns false
+// when the call would move more than kSmallMax bytes (nothing touched: the pool takes it).  With `discard`
+// the payload is not stored anywhere (Retire: the host already took it from the eager slot); every state
+// transition is that of Recv(cap).
+__device__ __forceinline__ bool svc_recv_small(const SvcParams& sp, int slot, uint8_t* dst, uint64_t capacity,
+                                               bool discard, OpResult& res, uint32_t lane) {
+  PairDev* Q = &sp.pairs[slot];
+  res.bytes = 0;
+  res.calls = 0;
+  if (VL(Q->status) != kStConnected) return true;  // pair.cc:266-268
+  const uint64_t cap = VL(Q->cap), mask = cap - 1;
+  uint8_t* ring = VL(Q->ring);
+  uint64_t head = VL(Q->head), mh = VL(Q->moving_head), remain = VL(Q->remain), acc = VL(Q->acc);
+  uint64_t r, src;
+  bool open;
+  if (remain > 0) {
+    r = remain;
+    src = mh;
+    open = false;
+  } else {  // GetReadableSize, ring_buffer.cc:67-97
+    const bool sys = VL(Q->wire) != 0;
+    const uint64_t hdr = sys ? ld_acquire_u64(ring + head) : ld_volatile_u64(ring + head);
+    if (hdr == 0 || hdr > cap - kReserved) return true;
+    const uint8_t* fp = ring + ((head + 8 + round_up8(hdr)) & mask);
+    const uint64_t foot = sys ? ld_acquire_u64(fp) : ld_volatile_u64(fp);
+    if (foot != kFooter) return true;
+    r = hdr;
+    src = (head + 8) & mask;
+    open = true;
+  }
+  const uint64_t n = r < capacity ? r : capacity;  // copy_size = min(readable, capacity)
+  if (n == 0) return true;
+  if (n > kSmallMax) return false;
+  if (!discard) warp_copy_from_ring(dst, ring, mask, src, (uint32_t)n, lane);
+  __syncwarp();
+  // clear-on-read: header (first touch), the bytes delivered, pad + footer when the frame is finished
+  const uint64_t end = (src + n) & mask;
+  uint64_t ztail = 0, mh_after = end;
+  if (n == r) {
+    const uint64_t up = round_up8(end);
+    ztail = (up - end) + 8;
+    mh_after = ((up & mask) + 8) & mask;
+  }
+  const uint64_t zhead = open ? 8 : 0;
+  warp_zero_ring(ring, mask, (src + cap - zhead) & mask, zhead + n + ztail, lane);
+  if (open) head = (head + 16 + round_up8(r)) & mask;  // ring_buffer.cc:140-141
+  remain = r - n;
+  acc += zhead + n + ztail;  // internal_bytes_read
+  bool credit = false;
+  if (acc >= cap / 2) {  // pair.cc:276-284
+    credit = true;
+    acc = 0;
+  }
+  __syncwarp();
+  if (credit) {
+    __threadfence_system();  // the sender may reuse the space only once it reads as zero
+    __syncwarp();
+    if (lane == 0) {
+      st_release_v2u64(VL(Q->peer_credit), mh_after, 0);  // updateStatus, pair.cc:624-641
+      PairMirror* pm = VL(Q->peer_mirror);
+      if (pm) ((volatile PairMirror*)pm)->credit_head = mh_after;
+    }
+  }
+  if (lane == 0) {
+    Q->head = head;
+    Q->moving_head = mh_after;
+    Q->remain = remain;
+    Q->acc = acc;
+    VL(sp.psvc[slot].delivered) = VL(sp.psvc[slot].delivered) + n;
+  }
+  __syncwarp();
+  __threadfence();
+  res.bytes = n;
+  res.calls = 1;
+  svc_rx_refresh(sp, Q, slot, true, lane);
+  return true;
+}
+
+struct OwnerShared {  // per owner warp
+  SvcCmd cmd[2];
+  int32_t box_a[kOwnBoxes], box_b[kOwnBoxes];  // pair slot of a job in flight (-1: box free) and its loopback peer
+  uint32_t box_kind[kOwnBoxes];
+};
+
+// reap finished pool jobs; when `slot_a`/`slot_b` >= 0 wait for every job that touches those pairs
+__device__ __forceinline__ void owner_reap(const SvcParams& sp, BigBox* boxes, OwnerShared& os, int slot_a, int slot_b,
+                                           uint32_t lane) {
+  if (lane < kOwnBoxes && os.box_a[lane] >= 0) {
+    const int a = os.box_a[lane], b = os.box_b[lane];
+    const bool must = (slot_a >= 0 && (a == slot_a || b == slot_a)) || (slot_b >= 0 && (a == slot_b || b == slot_b));
+    BigBox* bx = &boxes[lane];
+    uint32_t st = *(volatile uint32_t*)&bx->state;
+    while (must && st != 3) {
+      __nanosleep(100);
+      st = *(volatile uint32_t*)&bx->state;
+    }
+    if (st == 3) {
+      __threadfence();
+      if (os.box_kind[lane] == kSvcRecv) VL(sp.psvc[a].delivered) = VL(sp.psvc[a].delivered) + VL(bx->res.bytes);
+      os.box_a[lane] = -1;
+      *(volatile uint32_t*)&bx->state = 0;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) k_svc_owner(SvcParams sp) {
+  __shared__ OwnerShared s_os[4];
+  const uint32_t lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int q = blockIdx.x * 4 + wi;
+  if (q >= sp.nowners) return;
+  OwnerShared& os = s_os[wi];
+  const SvcCmd* qcmds = sp.cmds + (size_t)q * kOwnQ;
+  SvcDone* qdone = sp.done + (size_t)q * kOwnQ;
+  BigBox* boxes = sp.boxes + (size_t)q * kOwnBoxes;
+  if (lane < kOwnBoxes) os.box_a[lane] = os.box_b[lane] = -1;
+  __syncwarp();
+  uint32_t expect = 1, avail = 0, cur = 0, idle = 0;
+  while (true) {
+    // ---- fetch: entries `expect` and `expect + 1` in one trip (16 lanes x 16 bytes); both halves of a
+    // line carry the stamp because the two 64-byte halves may be read by separate PCIe reads
+    if (avail == 0) {
+      while (true) {
+        if (idle > 256) {  // nothing for a while: one small read per poll, then look properly
+          uint32_t st = 0;
+          if (lane == 0) st = ld_acquire_u32(&qcmds[(expect - 1) % kOwnQ].stamp);
+          st = __shfl_sync(0xffffffffu, st, 0);
+          if (st != expect) {
+            __nanosleep(400);
+            continue;
+          }
+        }
+        uint4 v = make_uint4(0, 0, 0, 0);
+        const uint32_t e = lane >> 3, ch = lane & 7;
+        if (lane < 16) v = ld_sys_v4(reinterpret_cast<const uint8_t*>(&qcmds[(expect - 1 + e) % kOwnQ]) + 16 * ch);
+        const bool okh = lane < 16 && ((ch == 0 && v.x == expect + e) || (ch == 7 && v.w == expect + e));
+        const unsigned okm = __ballot_sync(0xffffffffu, okh);
+        const bool ok0 = (okm & 0x81u) == 0x81u, ok1 = (okm & 0x8100u) == 0x8100u;
+        if (ok0) {
+          if (lane < 8 || (ok1 && lane < 16)) reinterpret_cast<uint4*>(&os.cmd[e])[ch] = v;
+          __syncwarp();
+          avail = ok1 ? 2 : 1;
+          cur = 0;
+          idle = 0;
+          break;
+        }
+        idle++;
+      }
+    }
+    const SvcCmd& c = os.cmd[cur];
+    const uint32_t opc = c.op;
+    if (opc == kSvcStop) break;
+    OpResult res;
+    res.bytes = 0;
+    res.calls = 0;
+    bool answer = true;
+    if (opc != kSvcNop) {
+      PairDev* P = &sp.pairs[c.slot];
+      const int peer = VL(P->peer_slot);
+      bool small = false;
+      if (opc == kSvcSend) {
+        uint64_t bytes = 0;
+        if (lane < c.nreal && lane < kSvcInline) bytes = c.inl[lane].len;
+        for (int o = 4; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        bytes = __shfl_sync(0xffffffffu, bytes, 0);
+        small = !(c.flags & kFlagUntilBlocked) && c.n <= kSvcInline && bytes <= kSmallMax;
+      } else {
+        small = !(c.flags & kFlagUntilBlocked);
+      }
+      bool done_small = false;
+      if (small) {
+        owner_reap(sp, boxes, os, c.slot, peer, lane);  // nothing of this connection may be in flight in the pool
+        if (opc == kSvcSend) {
+          svc_send_small(sp, c, res, lane);
+          done_small = true;
+        } else {
+          done_small = svc_recv_small(sp, c.slot, reinterpret_cast<uint8_t*>(c.ptr), c.n, opc == kSvcRetire, res, lane);
+        }
+      }
+      if (!done_small) {
+        // ---- hand the op to the pool; the CTA that runs it answers the host itself
+        owner_reap(sp, boxes, os, -1, -1, lane);
+        int bi = -1;
+        while (true) {
+          const unsigned freem = __ballot_sync(0xffffffffu, lane < kOwnBoxes && os.box_a[lane] < 0);
+          if (freem) {
+            bi = __ffs(freem) - 1;
+            break;
+          }
+          __nanosleep(200);
+          owner_reap(sp, boxes, os, -1, -1, lane);
+        }
+        BigBox* bx = &boxes[bi];
+        if (lane == 0) {
+          bx->kind = opc == kSvcSend ? kSvcSend : kSvcRecv;
+          bx->slot = c.slot;
+          bx->flags = c.flags | kFlagConcurrent;  // the two ends' jobs run side by side in the pool
+          bx->ptr = c.ptr;
+          bx->n = c.n;
+          bx->byte_idx = c.byte_idx;
+          bx->nreal = c.nreal;
+          bx->done = &qdone[(expect - 1) % kOwnQ];
+          bx->seq = expect;
+          os.box_a[bi] = c.slot;
+          os.box_b[bi] = peer;
+          os.box_kind[bi] = opc == kSvcSend ? kSvcSend : kSvcRecv;
+        }
+        if (lane < kSvcInline) bx->inl[lane] = c.inl[lane];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *(volatile uint32_t*)&bx->state = 1;
+        answer = false;
+      }
+    }
+    if (answer) {
+      // a Recv may have scattered into host memory from every lane: all of it before the answer
+      if (opc == kSvcRecv && res.bytes) __threadfence_system();
+      __syncwarp();
+      if (lane == 0) {
+        uint4 d;
+        d.x = (uint32_t)res.bytes;
+        d.y = (uint32_t)(res.bytes >> 32);
+        d.z = (uint32_t)res.calls;
+        d.w = expect;
+        st_sys_v4(&qdone[(expect - 1) % kOwnQ], d);
+      }
+    }
+    expect++;
+    cur++;
+    avail--;
+    __syncwarp();
+  }
+  // stop: wait for the pool jobs of this queue, then acknowledge
+  for (int i = 0; i < (int)kOwnBoxes; i++) {
+    if (lane == 0 && os.box_a[i] >= 0)
+      while (*(volatile uint32_t*)&boxes[i].state != 3) __nanosleep(200);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_system();
+    uint4 d = make_uint4(0, 0, 0, expect);
+    st_sys_v4(&qdone[(expect - 1) % kOwnQ], d);
+  }
+}
+
+// pool: CTAs with the k_send / k_recv machinery; a CTA claims a posted mailbox, runs the op and answers.
+__global__ void __launch_bounds__(kThreads, 2) k_svc_big(SvcParams sp) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
+  __shared__ PipeSmem pipe;
+  __shared__ OpResult s_res;
+  __shared__ int s_pick;
+  __shared__ uint32_t s_stop;
+  __shared__ __align__(16) BigBox s_box;
+  const uint32_t tid = threadIdx.x;
+  movers_init(pipe.bars, tid);
+  uint32_t phase_bits = 0;
+  const int nboxes = sp.nowners * (int)kOwnBoxes;
+  uint32_t idle = 0;
+  while (true) {
+    if (tid == 0) {
+      s_pick = 0x7fffffff;
+      s_stop = *(volatile uint32_t*)&sp.ps->stop;
+    }
+    __syncthreads();
+    if (s_stop) break;
+    for (int i = tid; i < nboxes; i += kThreads) {
+      const int b = (i + blockIdx.x * 37) % nboxes;  // CTAs start their scans at different boxes
+      if (*(volatile uint32_t*)&sp.boxes[b].state == 1) atomicMin(&s_pick, i);
+    }
+    __syncthreads();
+    int pick = s_pick;
+    __syncthreads();
+    if (pick != 0x7fffffff) {
+      const int b = (pick + blockIdx.x * 37) % nboxes;
+      if (tid == 0) s_pick = atomicCAS(&sp.boxes[b].state, 1u, 2u) == 1u ? b : -1;
+      __syncthreads();
+      pick = s_pick;
+      __syncthreads();
+    } else {
+      pick = -1;
+    }
+    if (pick < 0) {
+      if (++idle > 16) __nanosleep(idle > 4096 ? 2000 : 300);
+      continue;
+    }
+    idle = 0;
+    BigBox* bx = &sp.boxes[pick];
+    __threadfence();
+    // the mailbox was written from another SM: read it through to shared memory (never from a stale L1 line)
+    if (tid < sizeof(BigBox) / 16) reinterpret_cast<uint4*>(&s_box)[tid] = ld_sys_v4(reinterpret_cast<const uint4*>(bx) + tid);
+    if (tid == 0) {
+      s_res.bytes = 0;
+      s_res.calls = 0;
+    }
+    __syncthreads();
+    const uint32_t kind = s_box.kind;
+    if (kind == kSvcSend) {
+      SendOpDev op;
+      op.slot = s_box.slot;
+      op.flags = s_box.flags;
+      op.nslices = s_box.n;
+      op.slices = op.nslices <= kSvcInline ? s_box.inl : reinterpret_cast<const SliceDev*>(s_box.ptr);
+      op.byte_idx = s_box.byte_idx;
+      op.nreal = s_box.nreal;
+      send_body(sp.pairs, op, &s_res, pipe, stage_mem, phase_bits);
+    } else {
+      RecvOpDev op;
+      op.slot = s_box.slot;
+      op.flags = s_box.flags;
+      op.dst = reinterpret_cast<uint8_t*>(s_box.ptr);
+      op.cap = s_box.n;
+      recv_body(sp.pairs, op, &s_res, pipe, stage_mem, phase_bits);
+    }
+    // every byte this op produced must be visible before the answer: a Recv may have scattered into host
+    // memory from any mover; a Send only wrote host memory (the mirrors) under the mirror lock, whose release
+    // already fenced system-wide
+    if (kind == kSvcRecv) __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      bx->res = s_res;
+      uint4 d;
+      d.x = (uint32_t)s_res.bytes;
+      d.y = (uint32_t)(s_res.bytes >> 32);
+      d.z = (uint32_t)s_res.calls;
+      d.w = s_box.seq;
+      st_sys_v4(s_box.done, d);
+      __threadfence();
+      *(volatile uint32_t*)&bx->state = 3;
+    }
+    __syncthreads();
+  }
+}
+
+// resident poller of the BPEV design (Poller::begin_polling, poller.cc:52-106, and the engine's scan,
+// ev_epollex_rdma_bpev_linux.cc:1104-1145)
 __device__ __forceinline__ void service_poll_loop(PairDev* pairs, SvcPollState* ps, uint32_t* last_ev,
                                                   ReadyEntry* ready, uint32_t* host_scans) {
   const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -1215,74 +1813,8 @@ __device__ __forceinline__ void service_poll_loop(PairDev* pairs, SvcPollState* 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
-k_service(PairDev* __restrict__ pairs, SvcCmd* cmds, SvcDone* done, SvcPollState* ps, uint32_t* last_ev,
-          ReadyEntry* ready, uint32_t* host_scans, int nworkers) {
-  extern __shared__ __align__(128) uint8_t stage_mem[];
-  __shared__ PipeSmem pipe;
-  __shared__ SvcCmd s_cmd;
-  __shared__ OpResult s_res;
-  if ((int)blockIdx.x == nworkers) {
-    service_poll_loop(pairs, ps, last_ev, ready, host_scans);
-    return;
-  }
-  const uint32_t tid = threadIdx.x;
-  movers_init(pipe.bars, tid);
-  uint32_t phase_bits = 0;
-  SvcCmd* cmd = &cmds[blockIdx.x];
-  SvcDone* dn = &done[blockIdx.x];
-  uint32_t expect = 1;
-  while (true) {
-    if (tid == 0) {
-      uint32_t backoff = 0;
-      while (ld_acquire_u32(&cmd->seq) != expect)  // one PCIe read per poll
-        if (++backoff > 64) __nanosleep(100);
-      s_res.bytes = 0;
-      s_res.calls = 0;
-    }
-    __syncthreads();
-    if (tid < 8) {  // the whole 128-byte command in one trip: 8 lanes x 16 bytes
-      const uint4 v = ld_ring16(reinterpret_cast<const uint4*>(cmd) + tid);
-      reinterpret_cast<uint4*>(&s_cmd)[tid] = v;
-    }
-    __syncthreads();
-    const uint32_t opc = s_cmd.op;
-    if (opc == kSvcStop) break;
-    if (opc == kSvcSend) {
-      SendOpDev op;
-      op.slot = s_cmd.slot;
-      op.flags = s_cmd.flags;
-      op.slices = s_cmd.n <= kSvcInline ? s_cmd.inl : reinterpret_cast<const SliceDev*>(s_cmd.ptr);
-      op.nslices = s_cmd.n;
-      op.byte_idx = s_cmd.byte_idx;
-      send_body(pairs, op, &s_res, pipe, stage_mem, phase_bits);
-    } else if (opc == kSvcRecv) {
-      RecvOpDev op;
-      op.slot = s_cmd.slot;
-      op.flags = s_cmd.flags;
-      op.dst = reinterpret_cast<uint8_t*>(s_cmd.ptr);
-      op.cap = s_cmd.n;
-      recv_body(pairs, op, &s_res, pipe, stage_mem, phase_bits);
-    }
-    // every byte this op produced must be visible before the answer: a Recv may have scattered into
-    // host memory from any mover; a Send only wrote host memory (the mirrors) from thread 0, under the
-    // mirror lock, whose release already fenced system-wide
-    if (opc == kSvcRecv) __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      volatile SvcDone* vd = dn;
-      vd->bytes = s_res.bytes;
-      vd->calls = s_res.calls;
-      __threadfence_system();
-      vd->seq = expect;
-    }
-    expect++;
-    __syncthreads();
-  }
-  if (tid == 0) {
-    __threadfence_system();
-    *(volatile uint32_t*)&dn->seq = expect;  // stop acknowledged
-  }
+__global__ void __launch_bounds__(kThreads) k_svc_poll(SvcParams sp) {
+  service_poll_loop(sp.pairs, sp.ps, sp.last_ev, sp.ready, sp.host_scans);
 }
 
 // =========================================================================
@@ -1337,24 +1869,43 @@ k_probe_copy(uint8_t* __restrict__ dst, uint8_t* __restrict__ src, uint64_t byte
 }
 
 static void ensure_kernel_attrs() {
-  static bool done = false;
-  if (done) return;
-  done = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
   cudaFuncSetAttribute(k_send, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
   cudaFuncSetAttribute(k_recv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
   cudaFuncSetAttribute(k_probe_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
   cudaFuncSetAttribute(k_send, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(k_recv, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(k_probe_copy, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(k_service, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
-  cudaFuncSetAttribute(k_service, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_svc_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageTotal);
+  cudaFuncSetAttribute(k_svc_big, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  // Load every kernel of the library now.  With lazy module loading the first launch of a kernel loads it,
+  // and a load may wait for the device to go idle: beside a resident kernel that never happens.
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, k_send);
+  cudaFuncGetAttributes(&fa, k_recv);
+  cudaFuncGetAttributes(&fa, k_poll_scan);
+  cudaFuncGetAttributes(&fa, k_probe_copy);
+  cudaFuncGetAttributes(&fa, k_svc_owner);
+  cudaFuncGetAttributes(&fa, k_svc_big);
+  cudaFuncGetAttributes(&fa, k_svc_poll);
+  });
 }
 
-void launch_service(PairDev* pairs, SvcCmd* cmds, SvcDone* done, SvcPollState* ps, uint32_t* last_ev,
-                    ReadyEntry* ready, uint32_t* host_scans, int nworkers, void* stream) {
+bool launch_service(const SvcParams& sp, void* s_owner, void* s_big, void* s_poll) {
   ensure_kernel_attrs();
-  k_service<<<nworkers + 1, kThreads, kStageTotal, static_cast<cudaStream_t>(stream)>>>(
-      pairs, cmds, done, ps, last_ev, ready, host_scans, nworkers);
+  // all three grids stay resident and wait for each other's work: they must fit on the device together
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_svc_big, kThreads, kStageTotal) != cudaSuccess ||
+      sp.nbig + 2 > per_sm * sms)
+    return false;
+  const int octas = (sp.nowners + 3) / 4;
+  k_svc_owner<<<octas, 128, 0, static_cast<cudaStream_t>(s_owner)>>>(sp);
+  k_svc_big<<<sp.nbig, kThreads, kStageTotal, static_cast<cudaStream_t>(s_big)>>>(sp);
+  k_svc_poll<<<1, kThreads, 0, static_cast<cudaStream_t>(s_poll)>>>(sp);
+  return cudaGetLastError() == cudaSuccess;
 }
 
 void launch_probe_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,
@@ -1380,6 +1931,7 @@ void launch_recv(PairDev* pairs, const RecvOpDev* ops, OpResult* results, int no
 void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, uint32_t* ready_count,
                       int32_t* ready_slots, int n, void* stream) {
   if (n <= 0) return;
+  ensure_kernel_attrs();
   k_poll_scan<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(pairs, slots, events, ready_count,
                                                                                ready_slots, n);
 }

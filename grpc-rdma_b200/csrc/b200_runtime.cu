@@ -95,6 +95,14 @@ struct b200_pair {
   uint64_t* remote_credit = nullptr;
   std::string wire_file;  // this pair's descriptor under /dev/shm (unlinked on Disconnect)
   bool in_poller = false;
+  int max_sge = 30;  // captured at Init (what the kernels use for this pair)
+  // service: payload bytes Recv has returned since the service started (the device keeps the same count;
+  // an eagerly pushed frame is valid only while both agree), and the asynchronous Retire of the last
+  // eagerly received frame, if it has not been confirmed yet
+  uint64_t svc_delivered = 0;
+  std::atomic<bool> retire_pending{false};
+  int retire_q = 0;
+  uint64_t retire_ticket = 0;
 };
 
 constexpr int kLanes = 16;  // max internal lanes of the host-staged path (B200_LANES, default 8)
@@ -123,8 +131,11 @@ struct b200_batch {
   bool staged = false;
   uint8_t* d_stage = nullptr;
   std::vector<int> perm;  // perm[k] = caller's index of device op k
+  std::vector<b200_pair*> pairs;  // the pairs of a Recv batch (service: their eager records go stale at launch)
   LanePlan lanes[kLanes];
 };
+
+static void drain_retire(b200_pair* p);
 
 namespace {
 
@@ -176,34 +187,36 @@ struct Runtime {
   uint32_t* h_scan_count = nullptr;
   int32_t* h_scan_ready = nullptr;
   std::mutex scan_mu;
-  // persistent service kernel (b200_service_*)
-  struct SvcWorker {
-    std::mutex mu;
-    uint32_t seq = 0;
-    SliceDev* slices = nullptr;  // pinned, kMaxSgeLimit + 1 entries
-    uint8_t* bounce_tx = nullptr;
-    uint8_t* bounce_rx = nullptr;
-    uint64_t bounce_tx_cap = 0, bounce_rx_cap = 0;
+  // persistent service (b200_service_*): owner queues in pinned memory, pool mailboxes in HBM
+  struct OwnerQ {
+    std::mutex mu;          // posting only; nobody waits for an answer under it
+    uint64_t next = 0;      // next ticket
   };
   std::atomic<bool> svc_running{false};
-  int svc_workers = 0;
-  cudaStream_t svc_stream = nullptr;
-  SvcCmd* svc_cmds = nullptr;          // pinned, mapped
-  SvcDone* svc_done = nullptr;         // pinned, mapped
+  int svc_workers = 0;      // pool CTAs
+  int svc_nowners = 0;      // owner warps = command queues
+  cudaStream_t svc_stream = nullptr, svc_stream_big = nullptr, svc_stream_poll = nullptr;
+  OwnerQ* svc_q = nullptr;
+  SvcCmd* svc_cmds = nullptr;          // pinned, mapped  [nowners][kOwnQ]
+  SvcDone* svc_done = nullptr;         // pinned, mapped  [nowners][kOwnQ]
+  SliceDev* svc_slices = nullptr;      // pinned, mapped  [nowners][kOwnQ][kSvcSliceArea]
+  EagerRec* svc_erec = nullptr;        // pinned, mapped  [kMaxPairs]
+  uint8_t* svc_eslots = nullptr;       // pinned, mapped  [kMaxPairs][kEagerMax]
+  BigBox* d_svc_boxes = nullptr;
+  PairSvc* d_svc_psvc = nullptr;
   ReadyEntry* svc_ready = nullptr;     // pinned, mapped
   uint32_t* svc_host_scans = nullptr;  // pinned, mapped
   SvcPollState* d_svc_ps = nullptr;
   uint32_t* d_svc_last_ev = nullptr;
-  SvcWorker* svc_w = nullptr;
   uint32_t svc_hi_slot = 0;
-  std::atomic<uint64_t> svc_ops{0}, svc_ready_seen{0}, svc_ready_overflows{0};
+  std::atomic<uint64_t> svc_ops{0}, svc_ready_seen{0}, svc_ready_overflows{0}, svc_eager_hits{0};
   uint32_t svc_ready_head = 0;      // next stream index the host expects (under scan_mu)
   std::vector<uint16_t> svc_level;  // events pending per slot, as last reported by the device poller
   std::mutex grave_mu;
   std::vector<std::pair<void*, int>> graveyard;  // frees deferred while the persistent kernel runs
   // registry of memory this library handed out (skips cudaPointerGetAttributes on the unary path)
   std::mutex reg_mu;
-  std::map<uintptr_t, size_t> reg_ranges;
+  std::map<uintptr_t, std::pair<size_t, int>> reg_ranges;  // base -> (bytes, 1 = pinned host / 2 = device)
 };
 
 Runtime& R() {
@@ -229,17 +242,20 @@ bool write_setup(Runtime& r, b200_pair* p, const PairDev& hd) {
          CU_OK(cudaStreamSynchronize(r.stream));
 }
 
-// what kind of memory is this? 0 = unregistered host, 1 = GPU-addressable
-bool reg_has(const void* p);
-int mem_kind(const void* p) {
-  if (reg_has(p)) return 1;
+// what kind of memory is this? 0 = unregistered host, 1 = pinned / registered host, 2 = device or managed
+int reg_kind(const void* p);
+int mem_kind3(const void* p) {
+  const int k = reg_kind(p);
+  if (k) return k;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  return a.type == cudaMemoryTypeUnregistered ? 0 : 1;
+  if (a.type == cudaMemoryTypeUnregistered) return 0;
+  return a.type == cudaMemoryTypeHost ? 1 : 2;
 }
+int mem_kind(const void* p) { return mem_kind3(p) != 0; }  // 0 = unregistered host, 1 = GPU-addressable
 
 void kick(b200_pair* p) {
   if (p->wakeup_fd >= 0) (void)eventfd_write(p->wakeup_fd, 1);
@@ -259,10 +275,10 @@ void rt_free(void* p, int host) {
   else cudaFree(p);
 }
 
-void reg_add(const void* p, size_t n) {
+void reg_add(const void* p, size_t n, int kind) {
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.reg_mu);
-  r.reg_ranges[(uintptr_t)p] = n;
+  r.reg_ranges[(uintptr_t)p] = {n, kind};
 }
 void reg_del(const void* p) {
   Runtime& r = R();
@@ -286,16 +302,36 @@ std::string wire_path(uint32_t cookie, uint32_t qpn) {
   return b;
 }
 
-bool reg_has(const void* p) {
+// 0 = not in the registry, 1 = pinned host, 2 = device
+int reg_kind(const void* p) {
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.reg_mu);
   auto it = r.reg_ranges.upper_bound((uintptr_t)p);
-  if (it == r.reg_ranges.begin()) return false;
+  if (it == r.reg_ranges.begin()) return 0;
   --it;
-  return (uintptr_t)p < it->first + it->second;
+  return (uintptr_t)p < it->first + it->second.first ? it->second.second : 0;
 }
 
 }  // namespace
+
+// The calling thread's pinned bounce buffers for unregistered memory (several threads post to one queue at
+// the same time, so the staging cannot belong to the queue).  Released at b200_shutdown.
+struct TlsBounce {
+  uint8_t* tx = nullptr;
+  uint8_t* rx = nullptr;
+  uint64_t tx_cap = 0, rx_cap = 0;
+};
+static std::mutex g_tls_mu;
+static std::vector<TlsBounce*> g_tls_all;
+static TlsBounce& tls_bounce() {
+  static thread_local TlsBounce* t = nullptr;
+  if (!t) {
+    t = new TlsBounce();
+    std::lock_guard<std::mutex> lk(g_tls_mu);
+    g_tls_all.push_back(t);
+  }
+  return *t;
+}
 
 // =================================================================== runtime
 
@@ -405,6 +441,15 @@ extern "C" void b200_shutdown(void) {
   cudaFreeHost(r.h_scan_ready);
   if (r.bounce_tx) cudaFreeHost(r.bounce_tx);
   if (r.bounce_rx) cudaFreeHost(r.bounce_rx);
+  {
+    std::lock_guard<std::mutex> tl(g_tls_mu);
+    for (TlsBounce* t : g_tls_all) {
+      if (t->tx) cudaFreeHost(t->tx);
+      if (t->rx) cudaFreeHost(t->rx);
+      t->tx = t->rx = nullptr;
+      t->tx_cap = t->rx_cap = 0;
+    }
+  }
   r.bounce_tx = r.bounce_rx = nullptr;
   r.bounce_tx_cap = r.bounce_rx_cap = 0;
   cudaStreamDestroy(r.stream);
@@ -473,7 +518,7 @@ extern "C" void* b200_mem_alloc_device(size_t bytes) {
   void* p = nullptr;
   cudaSetDevice(R().dev);
   if (!CU_OK(cudaMalloc(&p, bytes ? bytes : 1))) return nullptr;
-  reg_add(p, bytes ? bytes : 1);
+  reg_add(p, bytes ? bytes : 1, 2);
   return p;
 }
 extern "C" void b200_mem_free_device(void* p) {
@@ -486,7 +531,7 @@ extern "C" void* b200_mem_alloc_host(size_t bytes) {
   void* p = nullptr;
   cudaSetDevice(R().dev);
   if (!CU_OK(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable))) return nullptr;
-  reg_add(p, bytes ? bytes : 1);
+  reg_add(p, bytes ? bytes : 1, 1);
   return p;
 }
 extern "C" void b200_mem_free_host(void* p) {
@@ -497,7 +542,7 @@ extern "C" void b200_mem_free_host(void* p) {
 extern "C" int b200_mem_register_host(void* p, size_t bytes) {
   if (!ensure_init()) return -1;
   if (!CU_OK(cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable))) return -1;
-  reg_add(p, bytes);
+  reg_add(p, bytes, 1);
   return 0;
 }
 extern "C" int b200_mem_unregister_host(void* p) {
@@ -593,6 +638,9 @@ extern "C" void b200_pair_init(b200_pair* p) {
   hd.status = B200_INITIALIZED;
   hd.max_sge = (uint32_t)r.cfg.max_sge;
   hd.peer_slot = -1;
+  p->max_sge = r.cfg.max_sge;
+  p->svc_delivered = 0;
+  p->retire_pending = false;
   memset(p->mirror, 0, sizeof(PairMirror));
   bool ok = CU_OK(cudaMemsetAsync(p->ring, 0, cap, r.stream)) &&  // RingBufferPollable::Init
             CU_OK(cudaMemcpyAsync(&r.d_pairs[p->slot], &hd, sizeof(hd), cudaMemcpyHostToDevice, r.stream)) &&
@@ -602,9 +650,14 @@ extern "C" void b200_pair_init(b200_pair* p) {
     p->status = B200_ERROR;
     return;
   }
-  if (r.svc_running.load() && (uint32_t)p->slot + 1 > r.svc_hi_slot) {
-    r.svc_hi_slot = (uint32_t)p->slot + 1;
-    cudaMemcpyAsync(&r.d_svc_ps->hi_slot, &r.svc_hi_slot, 4, cudaMemcpyHostToDevice, r.stream);
+  if (r.svc_running.load()) {
+    const PairSvc fresh{0, ~0ull};
+    memset((void*)&r.svc_erec[p->slot], 0, sizeof(EagerRec));
+    cudaMemcpyAsync(&r.d_svc_psvc[p->slot], &fresh, sizeof(fresh), cudaMemcpyHostToDevice, r.stream);
+    if ((uint32_t)p->slot + 1 > r.svc_hi_slot) {
+      r.svc_hi_slot = (uint32_t)p->slot + 1;
+      cudaMemcpyAsync(&r.d_svc_ps->hi_slot, &r.svc_hi_slot, 4, cudaMemcpyHostToDevice, r.stream);
+    }
     cudaStreamSynchronize(r.stream);
   }
   // drop a stale registration, then publish the new address
@@ -717,7 +770,7 @@ extern "C" int b200_pair_connect(b200_pair* p, const void* peer48, size_t n) {
     hd.mirror = p->mirror;
     hd.peer_mirror = nullptr;
     hd.status = B200_CONNECTED;
-    hd.max_sge = (uint32_t)r.cfg.max_sge;
+    hd.max_sge = (uint32_t)p->max_sge;
     hd.peer_slot = -1;
     hd.wire = 1;  // system-scope fences: the ring is in another GPU's HBM, reached over NVLink
     if (!write_setup(r, p, hd)) {
@@ -754,7 +807,7 @@ extern "C" int b200_pair_connect(b200_pair* p, const void* peer48, size_t n) {
   hd.mirror = p->mirror;
   hd.peer_mirror = q->mirror;
   hd.status = B200_CONNECTED;
-  hd.max_sge = (uint32_t)r.cfg.max_sge;
+  hd.max_sge = (uint32_t)p->max_sge;
   hd.peer_slot = q->slot;
   hd.wire = 0;
   if (!write_setup(r, p, hd)) {
@@ -772,6 +825,7 @@ extern "C" void b200_pair_disconnect(b200_pair* p) {
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.mu);
   if (p->status == B200_UNINITIALIZED || p->status == B200_DISCONNECTED) return;  // pair.cc:326-327
+  drain_retire(p);
   cudaSetDevice(r.dev);
   const bool was_connected = p->status == B200_CONNECTED && p->mirror->peer_exit == 0;
   if (was_connected && p->peer_local) {
@@ -841,6 +895,7 @@ extern "C" void b200_pair_consume_wakeup(b200_pair* p) {
 }
 extern "C" int b200_pair_has_message(const b200_pair* p) {
   if (!p) return 0;
+  drain_retire(const_cast<b200_pair*>(p));
   refresh_remote(p);
   return ((volatile PairMirror*)p->mirror)->has_message != 0;
 }
@@ -849,11 +904,13 @@ extern "C" int b200_pair_has_pending_writes(const b200_pair* p) {
 }
 extern "C" uint64_t b200_pair_readable(const b200_pair* p) {
   if (!p || p->status != B200_CONNECTED) return 0;  // pair.cc:290-292
+  drain_retire(const_cast<b200_pair*>(p));
   refresh_remote(p);
   return ((volatile PairMirror*)p->mirror)->readable;
 }
 extern "C" uint64_t b200_pair_writable(const b200_pair* p) {
   if (!p || !p->cap) return 0;
+  if (p->peer_local) drain_retire(p->peer_local);  // a Retire of the peer may return credit
   refresh_remote(p);
   volatile PairMirror* m = p->mirror;
   return writable_size(p->cap, m->credit_head, m->remote_tail);  // pair.cc:294-301
@@ -862,6 +919,8 @@ extern "C" uint64_t b200_pair_writable(const b200_pair* p) {
 extern "C" int b200_pair_get_state(b200_pair* p, b200_pair_state* out) {
   if (!p || !out || !ensure_init()) return -1;
   Runtime& r = R();
+  drain_retire(p);
+  if (p->peer_local) drain_retire(p->peer_local);
   std::lock_guard<std::mutex> lk(r.mu);
   cudaSetDevice(r.dev);
   PairDev hd;
@@ -880,6 +939,7 @@ extern "C" int b200_pair_get_state(b200_pair* p, b200_pair_state* out) {
 
 extern "C" int b200_pair_copy_ring(b200_pair* p, void* host_dst, uint64_t cap) {
   if (!p || !p->ring || cap < p->cap) return -1;
+  drain_retire(p);
   cudaSetDevice(R().dev);
   return CU_OK(cudaMemcpy(host_dst, p->ring, p->cap, cudaMemcpyDeviceToHost)) ? 0 : -1;
 }
@@ -895,72 +955,167 @@ static void refresh_remote(const b200_pair* cp);
 
 static bool ensure_bounce(uint8_t** buf, uint64_t* cap, uint64_t need);
 
+static int owner_of(const Runtime& r, const b200_pair* p) {
+  uint32_t key = (uint32_t)p->slot;
+  if (p->peer_local && (uint32_t)p->peer_local->slot < key) key = (uint32_t)p->peer_local->slot;  // both ends: one owner
+  return (int)(((key * 2654435761u) >> 12) % (uint32_t)r.svc_nowners);
+}
+
 extern "C" int b200_service_start(int workers) {
   if (!ensure_init()) return -1;
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.mu);
   if (r.svc_running.load()) return 0;
   if (workers <= 0) workers = (int)env_long("B200_SERVICE_WORKERS", 16);
-  if (workers > 128) workers = 128;
+  if (workers > 256) workers = 256;
+  int owners = (int)env_long("B200_SERVICE_OWNERS", 32);
+  if (owners < 1) owners = 1;
+  if (owners > 256) owners = 256;
   cudaSetDevice(r.dev);
   auto halloc = [&](void** p, size_t n) {
     if (!CU_OK(cudaHostAlloc(p, n, cudaHostAllocMapped | cudaHostAllocPortable))) return false;
     memset(*p, 0, n);
     return true;
   };
-  if (!r.svc_stream && !CU_OK(cudaStreamCreateWithFlags(&r.svc_stream, cudaStreamNonBlocking))) return -1;
-  if (!halloc((void**)&r.svc_cmds, sizeof(SvcCmd) * workers) || !halloc((void**)&r.svc_done, sizeof(SvcDone) * workers) ||
+  for (cudaStream_t* st : {&r.svc_stream, &r.svc_stream_big, &r.svc_stream_poll})
+    if (!*st && !CU_OK(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking))) return -1;
+  const size_t nent = (size_t)owners * kOwnQ;
+  if (!halloc((void**)&r.svc_cmds, sizeof(SvcCmd) * nent) || !halloc((void**)&r.svc_done, sizeof(SvcDone) * nent) ||
+      !halloc((void**)&r.svc_slices, sizeof(SliceDev) * nent * kSvcSliceArea) ||
+      !halloc((void**)&r.svc_erec, sizeof(EagerRec) * kMaxPairs) ||
+      !halloc((void**)&r.svc_eslots, (size_t)kEagerMax * kMaxPairs) ||
       !halloc((void**)&r.svc_ready, sizeof(ReadyEntry) * kReadyRing) || !halloc((void**)&r.svc_host_scans, 64))
     return -1;
-  if (!CU_OK(cudaMalloc(&r.d_svc_ps, sizeof(SvcPollState))) || !CU_OK(cudaMalloc(&r.d_svc_last_ev, 4 * kMaxPairs)))
+  if (!CU_OK(cudaMalloc(&r.d_svc_ps, sizeof(SvcPollState))) || !CU_OK(cudaMalloc(&r.d_svc_last_ev, 4 * kMaxPairs)) ||
+      !CU_OK(cudaMalloc(&r.d_svc_boxes, sizeof(BigBox) * owners * kOwnBoxes)) ||
+      !CU_OK(cudaMalloc(&r.d_svc_psvc, sizeof(PairSvc) * kMaxPairs)))
     return -1;
   r.svc_hi_slot = 0;
-  for (b200_pair* p : r.all_pairs)
+  for (b200_pair* p : r.all_pairs) {
     if ((uint32_t)p->slot + 1 > r.svc_hi_slot) r.svc_hi_slot = (uint32_t)p->slot + 1;
+    p->svc_delivered = 0;
+    p->retire_pending = false;
+  }
   SvcPollState ps{};
   ps.hi_slot = r.svc_hi_slot;
+  std::vector<PairSvc> psvc(kMaxPairs, PairSvc{0, ~0ull});
   if (!CU_OK(cudaMemcpyAsync(r.d_svc_ps, &ps, sizeof(ps), cudaMemcpyHostToDevice, r.stream)) ||
-      !CU_OK(cudaMemsetAsync(r.d_svc_last_ev, 0, 4 * kMaxPairs, r.stream)) || !CU_OK(cudaStreamSynchronize(r.stream)))
+      !CU_OK(cudaMemsetAsync(r.d_svc_last_ev, 0, 4 * kMaxPairs, r.stream)) ||
+      !CU_OK(cudaMemsetAsync(r.d_svc_boxes, 0, sizeof(BigBox) * owners * kOwnBoxes, r.stream)) ||
+      !CU_OK(cudaMemcpyAsync(r.d_svc_psvc, psvc.data(), sizeof(PairSvc) * kMaxPairs, cudaMemcpyHostToDevice, r.stream)) ||
+      !CU_OK(cudaStreamSynchronize(r.stream)))
     return -1;
-  r.svc_w = new Runtime::SvcWorker[workers];
-  for (int w = 0; w < workers; w++)
-    if (!halloc((void**)&r.svc_w[w].slices, sizeof(SliceDev) * (kMaxSgeLimit + 1))) return -1;
+  r.svc_q = new Runtime::OwnerQ[owners];
   r.svc_workers = workers;
+  r.svc_nowners = owners;
   r.svc_ready_head = 0;
   r.svc_level.assign(kMaxPairs, 0);
-  launch_service(r.d_pairs, r.svc_cmds, r.svc_done, r.d_svc_ps, r.d_svc_last_ev, r.svc_ready, r.svc_host_scans, workers,
-                 r.svc_stream);
-  r.launches++;
-  if (!CU_OK(cudaGetLastError())) return -1;
+  SvcParams sp{};
+  sp.pairs = r.d_pairs;
+  sp.psvc = r.d_svc_psvc;
+  sp.cmds = r.svc_cmds;
+  sp.done = r.svc_done;
+  sp.boxes = r.d_svc_boxes;
+  sp.erec = env_long("B200_SERVICE_EAGER", 1) ? r.svc_erec : nullptr;
+  sp.eslots = r.svc_eslots;
+  sp.ps = r.d_svc_ps;
+  sp.last_ev = r.d_svc_last_ev;
+  sp.ready = r.svc_ready;
+  sp.host_scans = r.svc_host_scans;
+  sp.nowners = owners;
+  sp.nbig = workers;
+  if (!launch_service(sp, r.svc_stream, r.svc_stream_big, r.svc_stream_poll)) {
+    set_err("b200_service_start: the resident kernels (" + std::to_string(workers) +
+            " pool CTAs + owners + poller) do not fit on the device together");
+    cudaGetLastError();
+    return -1;
+  }
+  r.launches += 3;
   r.svc_running = true;
   return 0;
 }
 
 extern "C" int b200_service_running(void) { return R().svc_running.load() ? R().svc_workers : 0; }
 
+// ---- owner queues: post = claim the next ticket of the queue and fill its entry; the answer lands in the
+// entry's SvcDone.  An entry is reused every kOwnQ tickets, once the answer of its previous ticket was seen.
+template <class Fill>
+static uint64_t svc_post(Runtime& r, int q, Fill fill) {
+  Runtime::OwnerQ& Q = r.svc_q[q];
+  std::lock_guard<std::mutex> lk(Q.mu);
+  const uint64_t t = Q.next++;
+  const size_t e = (size_t)q * kOwnQ + t % kOwnQ;
+  volatile SvcDone* d = &r.svc_done[e];
+  if (t >= kOwnQ)
+    while (d->seq != (uint32_t)(t - kOwnQ + 1)) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  SvcCmd* c = &r.svc_cmds[e];
+  c->nreal = 0;
+  fill(c, r.svc_slices + e * kSvcSliceArea);
+  std::atomic_thread_fence(std::memory_order_release);
+  *(volatile uint32_t*)&c->stamp2 = (uint32_t)(t + 1);
+  *(volatile uint32_t*)&c->stamp = (uint32_t)(t + 1);
+  return t;
+}
+
+static bool svc_wait(Runtime& r, int q, uint64_t t, uint64_t* bytes, uint64_t* calls) {
+  volatile SvcDone* d = &r.svc_done[(size_t)q * kOwnQ + t % kOwnQ];
+  const uint32_t want = (uint32_t)(t + 1);
+  uint32_t spins = 0;
+  std::chrono::steady_clock::time_point t0;
+  // (an entry can only be reused after this answer was seen by the poster of ticket t + kOwnQ, which is
+  // blocked behind us in svc_post: the stamp stays until we have read it -- unless somebody else waits for
+  // the same ticket, which only drain_retire does, under the pair's own ordering)
+  while (d->seq != want) {
+    if ((int32_t)(d->seq - want) > 0) break;  // already reused: the answer was seen (Retire has no result)
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xfffff) == 0) {
+      if (spins == 0x100000) t0 = std::chrono::steady_clock::now();
+      else if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) {
+        set_err("b200 service: command timed out");
+        return false;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (bytes) *bytes = d->bytes;
+  if (calls) *calls = d->calls;
+  r.svc_ops++;
+  return true;
+}
+
+// the asynchronous Retire of the last eagerly received frame must have run before anything looks at the
+// pair's receive side again (mirror, state, ring image) -- it is a couple of microseconds behind at most
+static void drain_retire(b200_pair* p) {
+  if (!p->retire_pending.load(std::memory_order_acquire)) return;
+  Runtime& r = R();
+  if (r.svc_running.load()) svc_wait(r, p->retire_q, p->retire_ticket, nullptr, nullptr);
+  p->retire_pending.store(false, std::memory_order_release);
+}
+
 extern "C" void b200_service_stop(void) {
   Runtime& r = R();
   if (!r.inited || !r.svc_running.load()) return;
   cudaSetDevice(r.dev);
-  for (int w = 0; w < r.svc_workers; w++) {
-    std::lock_guard<std::mutex> lk(r.svc_w[w].mu);
-    SvcCmd* c = &r.svc_cmds[w];
-    c->op = kSvcStop;
-    std::atomic_thread_fence(std::memory_order_release);
-    *(volatile uint32_t*)&c->seq = ++r.svc_w[w].seq;
+  for (b200_pair* p : r.all_pairs) drain_retire(p);
+  for (int q = 0; q < r.svc_nowners; q++) {
+    const uint64_t t = svc_post(r, q, [&](SvcCmd* c, SliceDev*) { c->op = kSvcStop; });
+    svc_wait(r, q, t, nullptr, nullptr);  // the owner has left (its pool jobs are finished)
   }
   uint32_t one = 1;
   cudaMemcpyAsync(&r.d_svc_ps->stop, &one, 4, cudaMemcpyHostToDevice, r.stream);
   cudaStreamSynchronize(r.stream);
-  cudaStreamSynchronize(r.svc_stream);  // the kernel exits
+  cudaStreamSynchronize(r.svc_stream);  // the kernels exit
+  cudaStreamSynchronize(r.svc_stream_big);
+  cudaStreamSynchronize(r.svc_stream_poll);
   r.svc_running = false;
-  for (int w = 0; w < r.svc_workers; w++) {
-    cudaFreeHost(r.svc_w[w].slices);
-    if (r.svc_w[w].bounce_tx) cudaFreeHost(r.svc_w[w].bounce_tx);
-    if (r.svc_w[w].bounce_rx) cudaFreeHost(r.svc_w[w].bounce_rx);
-  }
-  delete[] r.svc_w;
-  r.svc_w = nullptr;
+  delete[] r.svc_q;
+  r.svc_q = nullptr;
   {
     // the host poller thread reads the ready ring under scan_mu: hand it a null pointer before the free
     std::lock_guard<std::mutex> lk(r.scan_mu);
@@ -970,15 +1125,26 @@ extern "C" void b200_service_stop(void) {
   }
   cudaFreeHost(r.svc_cmds);
   cudaFreeHost(r.svc_done);
+  cudaFreeHost(r.svc_slices);
+  cudaFreeHost(r.svc_erec);
+  cudaFreeHost(r.svc_eslots);
   cudaFreeHost(r.svc_host_scans);
   cudaFree(r.d_svc_ps);
   cudaFree(r.d_svc_last_ev);
+  cudaFree(r.d_svc_boxes);
+  cudaFree(r.d_svc_psvc);
   r.svc_cmds = nullptr;
   r.svc_done = nullptr;
+  r.svc_slices = nullptr;
+  r.svc_erec = nullptr;
+  r.svc_eslots = nullptr;
   r.svc_host_scans = nullptr;
   r.d_svc_ps = nullptr;
   r.d_svc_last_ev = nullptr;
+  r.d_svc_boxes = nullptr;
+  r.d_svc_psvc = nullptr;
   r.svc_workers = 0;
+  r.svc_nowners = 0;
   std::vector<std::pair<void*, int>> dead;
   {
     std::lock_guard<std::mutex> lk(r.grave_mu);
@@ -999,46 +1165,21 @@ extern "C" void b200_service_stats(uint64_t out[4]) {
   out[2] = r.svc_ready_overflows.load();
   out[3] = r.svc_host_scans ? *(volatile uint32_t*)r.svc_host_scans : 0;
 }
+extern "C" uint64_t b200_service_eager_hits(void) { return R().svc_eager_hits.load(); }
 
-// post one command to the worker that owns the pair and wait for its answer
-static bool svc_call(Runtime& r, Runtime::SvcWorker& w, int wi, uint32_t op, int slot, uint64_t ptr, uint64_t n,
-                     uint64_t byte_idx, uint64_t* bytes) {
-  SvcCmd* c = &r.svc_cmds[wi];
-  volatile SvcDone* d = &r.svc_done[wi];
-  c->op = op;
-  c->slot = slot;
-  c->flags = B200_BATCH_ONE_CALL | B200_BATCH_CONCURRENT;  // the two ends' workers run side by side
-  c->ptr = ptr;
-  c->n = n;
-  c->byte_idx = byte_idx;
-  const uint32_t seq = ++w.seq;
-  std::atomic_thread_fence(std::memory_order_release);
-  *(volatile uint32_t*)&c->seq = seq;
-  const auto t0 = std::chrono::steady_clock::now();
-  uint32_t spins = 0;
-  while (d->seq != seq) {
-#if defined(__x86_64__)
-    __builtin_ia32_pause();
-#endif
-    if ((++spins & 0xfffff) == 0 &&
-        std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) {
-      set_err("b200 service: command timed out");
-      return false;
-    }
-  }
-  std::atomic_thread_fence(std::memory_order_acquire);
-  *bytes = d->bytes;
-  r.svc_ops++;
-  return true;
-}
-
-static uint64_t svc_send(Runtime& r, b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
-  const int wi = p->slot % r.svc_workers;
-  Runtime::SvcWorker& w = r.svc_w[wi];
-  std::lock_guard<std::mutex> lk(w.mu);
-  const size_t look = n < (size_t)r.cfg.max_sge ? n : (size_t)r.cfg.max_sge;
+// fill the slice list of a Send command: <= max_sge slices are looked at by one call, the rest only counts
+// towards total_slice_size (pair.cc:661-664) and is folded into one pseudo-slice that is never dereferenced
+// (SvcCmd.nreal); unregistered memory is staged in the calling thread's pinned bounce buffer
+static bool svc_fill_send(b200_pair* p, SvcCmd* c, SliceDev* area, const b200_slice* slices, size_t n, size_t byte_idx,
+                          uint32_t flags) {
+  size_t look = n;
+  if (!(flags & B200_BATCH_UNTIL_BLOCKED) && look > (size_t)p->max_sge) look = (size_t)p->max_sge;
+  if (look > kSvcSliceArea - 1) look = kSvcSliceArea - 1;
   uint64_t rest = 0;
   for (size_t i = look; i < n; i++) rest += slices[i].len;
+  const size_t nsl = look + (rest ? 1 : 0);
+  SliceDev* out = nsl <= kSvcInline ? c->inl : area;
+  TlsBounce& tb = tls_bounce();
   uint64_t bounce_off = 0;
   for (size_t i = 0; i < look; i++) {
     const uint8_t* ptr = (const uint8_t*)slices[i].ptr;
@@ -1046,27 +1187,41 @@ static uint64_t svc_send(Runtime& r, b200_pair* p, const b200_slice* slices, siz
     if (len && mem_kind(ptr) == 0) {  // unregistered host memory: stage like the reference's send buffer
       const uint64_t skip = i == 0 ? byte_idx : 0;
       const uint64_t useful = len - skip;
-      const uint64_t limit = p->cap / 2;
+      const uint64_t limit = p->cap / 2;  // a call never accepts more than the staging size
       uint64_t take = useful < limit ? useful : limit;
-      if (!ensure_bounce(&w.bounce_tx, &w.bounce_tx_cap, p->cap + 16 * (kMaxSgeLimit + 4))) return 0;
-      if (bounce_off + take > w.bounce_tx_cap) take = w.bounce_tx_cap - bounce_off;
-      memcpy(w.bounce_tx + bounce_off, ptr + skip, take);
-      w.slices[i].ptr = w.bounce_tx + bounce_off - skip;
+      if (!ensure_bounce(&tb.tx, &tb.tx_cap, p->cap + 16 * (kMaxSgeLimit + 4))) return false;
+      if (bounce_off + take > tb.tx_cap) take = tb.tx_cap - bounce_off;
+      memcpy(tb.tx + bounce_off, ptr + skip, take);
+      out[i].ptr = tb.tx + bounce_off - skip;  // keep (ptr + skip) pointing at the staged bytes
       bounce_off += (take + 15) & ~15ull;
     } else {
-      w.slices[i].ptr = ptr;
+      out[i].ptr = ptr;
     }
-    w.slices[i].len = len;
+    out[i].len = len;
   }
-  size_t nsl = look;
   if (rest) {
-    w.slices[nsl].ptr = nullptr;
-    w.slices[nsl].len = rest;
-    nsl++;
+    out[look].ptr = nullptr;
+    out[look].len = rest;
   }
-  if (nsl <= kSvcInline) memcpy(r.svc_cmds[wi].inl, w.slices, sizeof(SliceDev) * nsl);
+  c->op = kSvcSend;
+  c->slot = p->slot;
+  c->flags = flags;
+  c->ptr = (uint64_t)(uintptr_t)area;
+  c->n = nsl;
+  c->nreal = (uint32_t)look;
+  c->byte_idx = byte_idx;
+  return true;
+}
+
+static uint64_t svc_send(Runtime& r, b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
+  const int q = owner_of(r, p);
+  bool ok = true;
+  const uint64_t t = svc_post(r, q, [&](SvcCmd* c, SliceDev* area) {
+    ok = svc_fill_send(p, c, area, slices, n, byte_idx, B200_BATCH_ONE_CALL);
+    if (!ok) c->op = kSvcNop;
+  });
   uint64_t bytes = 0;
-  if (!svc_call(r, w, wi, kSvcSend, p->slot, (uint64_t)(uintptr_t)w.slices, nsl, byte_idx, &bytes)) {
+  if (!svc_wait(r, q, t, &bytes, nullptr) || !ok) {
     p->error = t_err;
     p->status = B200_ERROR;
     return 0;
@@ -1074,25 +1229,72 @@ static uint64_t svc_send(Runtime& r, b200_pair* p, const b200_slice* slices, siz
   return bytes;
 }
 
+static uint64_t eager_checksum(const uint8_t* slot, uint32_t size, uint64_t at) {
+  uint64_t cs = eager_mix(at * 31 + size);
+  const uint32_t words = (size + 7) >> 3;
+  for (uint32_t j = 0; j < words; j++) {
+    uint64_t w = *(const volatile uint64_t*)(slot + 8ull * j);
+    const uint32_t rem = size - 8 * j;
+    if (rem < 8) w &= (1ull << (8 * rem)) - 1;
+    cs ^= eager_word(w, j);
+  }
+  return cs;
+}
+
 static uint64_t svc_recv(Runtime& r, b200_pair* p, void* dst, uint64_t cap) {
-  const int wi = p->slot % r.svc_workers;
-  Runtime::SvcWorker& w = r.svc_w[wi];
-  std::lock_guard<std::mutex> lk(w.mu);
-  const bool bounce = mem_kind(dst) == 0;
+  const int q = owner_of(r, p);
+  const int kind = mem_kind3(dst);
+  // ---- eager: the frame at the head of the ring was already pushed to this pair's host slot by the kernel
+  // that landed it (or that retired its predecessor): take it from there, retire it asynchronously
+  if (r.svc_erec && kind != 2 && !p->remote) {
+    volatile EagerRec* rec = &r.svc_erec[p->slot];
+    const uint8_t* slot = r.svc_eslots + (size_t)p->slot * kEagerMax;
+    for (int attempt = 0; attempt < 4; attempt++) {
+      const uint64_t at = rec->at;
+      const uint32_t size = rec->size;
+      if (rec->magic != kEagerMagic || at != p->svc_delivered || size == 0 || size > kEagerMax || size > cap) break;
+      const uint64_t cs = rec->csum;
+      memcpy(dst, slot, size);
+      if (eager_checksum((const uint8_t*)dst, size, at) != cs) continue;  // payload stores still in flight: look again
+      p->svc_delivered += size;
+      p->retire_q = q;
+      p->retire_ticket = svc_post(r, q, [&](SvcCmd* c, SliceDev*) {
+        c->op = kSvcRetire;
+        c->slot = p->slot;
+        c->flags = B200_BATCH_ONE_CALL;
+        c->ptr = 0;
+        c->n = size;
+        c->byte_idx = 0;
+      });
+      p->retire_pending.store(true, std::memory_order_release);
+      r.svc_eager_hits++;
+      return size;
+    }
+  }
   uint8_t* kdst = (uint8_t*)dst;
   uint64_t kcap = cap;
-  if (bounce) {
-    if (kcap > p->cap) kcap = p->cap;
-    if (!ensure_bounce(&w.bounce_rx, &w.bounce_rx_cap, p->cap)) return 0;
-    kdst = w.bounce_rx;
+  TlsBounce& tb = tls_bounce();
+  if (kind == 0) {
+    if (kcap > p->cap) kcap = p->cap;  // one frame never exceeds the ring
+    if (!ensure_bounce(&tb.rx, &tb.rx_cap, p->cap)) return 0;
+    kdst = tb.rx;
   }
+  const uint64_t t = svc_post(r, q, [&](SvcCmd* c, SliceDev*) {
+    c->op = kSvcRecv;
+    c->slot = p->slot;
+    c->flags = B200_BATCH_ONE_CALL;
+    c->ptr = (uint64_t)(uintptr_t)kdst;
+    c->n = kcap;
+    c->byte_idx = 0;
+  });
   uint64_t bytes = 0;
-  if (!svc_call(r, w, wi, kSvcRecv, p->slot, (uint64_t)(uintptr_t)kdst, kcap, 0, &bytes)) {
+  if (!svc_wait(r, q, t, &bytes, nullptr)) {
     p->error = t_err;
     p->status = B200_ERROR;
     return 0;
   }
-  if (bounce && bytes) memcpy(dst, w.bounce_rx, bytes);
+  p->svc_delivered += bytes;
+  if (kind == 0 && bytes) memcpy(dst, tb.rx, bytes);
   return bytes;
 }
 
@@ -1125,6 +1327,7 @@ extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_
   if (!p || !ensure_init()) return 0;
   Runtime& r = R();
   if (p->status == B200_CONNECTED && n) {
+    if (p->peer_local) drain_retire(p->peer_local);  // its Retire may be about to return credit
     refresh_remote(p);
     if (send_is_a_no_op(p)) return 0;
   }
@@ -1143,7 +1346,7 @@ extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_
   // One Send call looks at <= max_sge slices; the rest only contributes to
   // total_slice_size (pair.cc:661-664), folded into one trailing pseudo-slice
   // that is never dereferenced.
-  const size_t look = n < (size_t)r.cfg.max_sge ? n : (size_t)r.cfg.max_sge;
+  const size_t look = n < (size_t)p->max_sge ? n : (size_t)p->max_sge;
   uint64_t rest = 0;
   for (size_t i = look; i < n; i++) rest += slices[i].len;
   uint64_t bounce_off = 0;
@@ -1177,6 +1380,7 @@ extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_
   r.h_sop->flags = B200_BATCH_ONE_CALL;
   r.h_sop->slices = r.h_slices;
   r.h_sop->nslices = nsl;
+  r.h_sop->nreal = look;
   r.h_sop->byte_idx = byte_idx;
   r.h_res->bytes = 0;
   r.h_res->calls = 0;
@@ -1193,6 +1397,7 @@ extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_
 extern "C" uint64_t b200_pair_recv(b200_pair* p, void* dst, uint64_t cap) {
   if (!p || !ensure_init()) return 0;
   Runtime& r = R();
+  drain_retire(p);
   // same reasoning for a Recv on a ring the mirror shows empty: it delivers nothing, changes nothing
   if (p->status == B200_CONNECTED && !p->remote && ((volatile PairMirror*)p->mirror)->has_message == 0) return 0;
   if (r.svc_running.load()) {
@@ -1281,7 +1486,7 @@ static void push_h2d(std::vector<CopyRun>& out, uint8_t* stage, const uint8_t* s
       lead = 0;  // memory registered by someone else: its base is unknown
     } else {
       --it;
-      if ((uintptr_t)src >= it->first + it->second || (uintptr_t)src - lead < it->first) lead = 0;
+      if ((uintptr_t)src >= it->first + it->second.first || (uintptr_t)src - lead < it->first) lead = 0;
     }
   }
   out.push_back({stage - lead, src - lead, lead + bytes});
@@ -1358,6 +1563,7 @@ static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int 
       h[k].flags = kflags;
       h[k].slices = b->d_slices + off;
       h[k].nslices = o.nslices;
+      h[k].nreal = o.nslices;
       h[k].byte_idx = o.byte_idx;
       const int L = b->staged ? lane_of(o.pair) : 0;
       const uint8_t* run_end = nullptr;
@@ -1400,10 +1606,12 @@ static b200_batch* prepare_common(int kind, const void* ops_v, size_t nops, int 
       h[k].flags = kflags;
       h[k].dst = (uint8_t*)o.dst;
       h[k].cap = o.cap;
+      b->pairs.push_back(o.pair);
       if (b->staged && o.cap) place[k] = stage_place(cursor, o.dst, o.cap);
     }
     if (ok && b->staged) {
-      ok = CU_OK(cudaMalloc(&b->d_stage, cursor + kDmaAlign));
+      // zeroed once: the whole destination window is copied back, whatever was delivered into it
+      ok = CU_OK(cudaMalloc(&b->d_stage, cursor + kDmaAlign)) && CU_OK(cudaMemset(b->d_stage, 0, cursor + kDmaAlign));
       for (size_t k = 0; ok && k < nops; k++) {
         const b200_recv_op& o = rops[b->perm[k]];
         if (!o.cap) continue;
@@ -1463,6 +1671,15 @@ extern "C" int b200_batch_launch(b200_batch* b, void* stream) {
   if (!b) return -1;
   Runtime& r = R();
   if (b->nops == 0) return 0;
+  if (b->kind == 1 && r.svc_running.load()) {
+    // frames are about to be consumed behind the service's back: whatever it pushed eagerly for these pairs
+    // is stale from now on, and stays so (host and device counts no longer agree -> Recv takes the normal path)
+    for (b200_pair* p : b->pairs) {
+      drain_retire(p);
+      ((volatile EagerRec*)&r.svc_erec[p->slot])->magic = 0;
+      p->svc_delivered += 1ull << 40;
+    }
+  }
   if (!b->staged) {
     cudaStream_t s = stream ? (cudaStream_t)stream : r.stream;
     if (b->kind == 0) launch_send(r.d_pairs, (const SendOpDev*)b->d_ops, b->d_results, b->nops, s);

@@ -197,6 +197,8 @@ int b200_service_running(void); /* number of worker CTAs, 0 = not running */
 /* out[0] commands executed, [1] ready-ring entries consumed, [2] ready-ring overruns,
  * [3] device poller scans (updated every 1024 scans) */
 void b200_service_stats(uint64_t out[4]);
+/* Recv calls answered from a pair's eagerly pushed host slot (no trip to the GPU and back). */
+uint64_t b200_service_eager_hits(void);
 
 /* ------------------------------------------------------------------- batch */
 /*

@@ -16,6 +16,7 @@ cp $ROOT/integration/stack/infiniband/verbs.h $PFX/include/infiniband/verbs.h
 cp $ROOT/integration/stack/hdr/hdr_histogram.h $PFX/include/hdr/hdr_histogram.h
 g++ -O2 -g -fPIC -shared -std=c++14 -I$PFX/include -o $PFX/lib/libibverbs.so $ROOT/oracle/shim/fake_verbs.cc $ROOT/integration/stack/verbs_event_stubs.cc -lpthread
 gcc -O2 -g -fPIC -shared -I$PFX/include -o $PFX/lib/libhdr_histogram.so $ROOT/integration/stack/hdr_histogram_mini.c
+export CPLUS_INCLUDE_PATH=$PFX/include C_INCLUDE_PATH=$PFX/include  # grpc++ sources reach infiniband/verbs.h through core headers
 cd $OUT/grpc
 if [ ! -f build.ninja ]; then
   cmake -G Ninja $REF -DCMAKE_POLICY_VERSION_MINIMUM=3.5 -DCMAKE_BUILD_TYPE=Release \
