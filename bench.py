@@ -516,7 +516,7 @@ def run_unary(args, pkg, L, with_cpu):
     pkg.config_set("GRPC_RDMA_RING_BUFFER_SIZE_KB", 4096)   # the reference's default ring (config.cc:90-96)
     out = {"msg_bytes": m, "ring_kb": 4096, "b200": {}, "cpu_reference": None,
            "path": "b200_pair_send / has_message / recv on registered host buffers, persistent service kernel "
-                   "(%d worker CTAs + 1 poller CTA)" % args.service_workers}
+                   "(owner warps + %d pool CTAs + poller)" % args.service_workers}
     launches0 = L.b200_launch_count()
     if L.b200_service_start(args.service_workers) != 0:
         return {"error": "b200_service_start: " + pkg.last_error()}
@@ -534,7 +534,8 @@ def run_unary(args, pkg, L, with_cpu):
             out["b200"]["conns_%d" % conns] = d
     finally:
         L.b200_service_stop()
-    out["kernel_launches_during_unary"] = int(L.b200_launch_count() - launches0)   # 1 = the service kernel itself
+    out["kernel_launches_during_unary"] = int(L.b200_launch_count() - launches0)   # 3 = the resident kernels themselves
+    out["eager_recvs"] = int(L.b200_service_eager_hits())
     if with_cpu:
         try:
             eng, kind = cpu_engine()

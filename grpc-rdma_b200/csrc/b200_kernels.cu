@@ -1183,37 +1183,53 @@ __device__ __forceinline__ uint8_t ld_volatile_u8(const void* p) { return *(cons
 // n bytes from `src` (any alignment; device or pinned host memory: system-coherent loads that bypass
 // L1, the host reuses its buffers) into the ring at payload offset `off` (8-byte aligned; wraps at
 // cap).  Whole 8-byte words are written, the tail padded with zeros (pad bytes are never delivered).
-__device__ __forceinline__ void warp_copy_to_ring(uint8_t* ring, uint64_t mask, uint64_t off, const uint8_t* src,
-                                                  uint32_t n, uint32_t lane) {
+// With `eslot` the words also go to that host slot and their eager checksum contribution is returned.
+constexpr int kCopyBatch = 8;  // 8-byte words per lane whose loads are in flight together (2 KiB per warp)
+
+__device__ __forceinline__ uint64_t warp_copy_to_ring(uint8_t* ring, uint64_t mask, uint64_t off, const uint8_t* src,
+                                                      uint32_t n, uint8_t* eslot, uint32_t lane) {
   const uintptr_t s = reinterpret_cast<uintptr_t>(src);
   const uint32_t sb = (uint32_t)(s & 7), sh = sb * 8;
   const uint64_t* s0 = reinterpret_cast<const uint64_t*>(s & ~(uintptr_t)7);
   const uint32_t words = (n + 7) >> 3;
-  for (uint32_t base = 0; base < words; base += 32) {
-    const uint32_t j = base + lane;
-    const bool act = j < words;
-    uint64_t lo = 0, hi = 0;
-    if (act) lo = ld_sys_u64(s0 + j);
-    const uint64_t nxt = __shfl_down_sync(0xffffffffu, lo, 1);
-    uint64_t w = lo;
-    if (sh) {
-      // the last payload byte of word j is byte min(8 j + 8, n) - 1; it lives in aligned word (sb + b) / 8
-      const uint32_t lastb = (8 * j + 8 < n ? 8 * j + 8 : n) - 1;
-      const bool need_hi = act && (sb + lastb) / 8 > j;
-      if (need_hi) hi = (lane == 31 || j + 1 >= words) ? ld_sys_u64(s0 + j + 1) : nxt;
-      w = (lo >> sh) | (hi << (64 - sh));
+  uint64_t cs = 0;
+  for (uint32_t base = 0; base < words; base += 32 * kCopyBatch) {
+    // all loads of the batch first (one trip over PCIe for host slices), then shifts and stores
+    uint64_t lo[kCopyBatch], hi[kCopyBatch];
+#pragma unroll
+    for (int k = 0; k < kCopyBatch; k++) {
+      const uint32_t j = base + 32 * k + lane;
+      lo[k] = j < words ? ld_sys_u64(s0 + j) : 0;
     }
-    if (act) {
-      const uint32_t rem = n - 8 * j;
-      if (rem < 8) w &= (1ull << (8 * rem)) - 1;
-      *reinterpret_cast<uint64_t*>(ring + ((off + 8ull * j) & mask)) = w;
+    if (sh) {
+#pragma unroll
+      for (int k = 0; k < kCopyBatch; k++) {
+        const uint32_t j = base + 32 * k + lane;
+        // the last payload byte of word j is byte min(8 j + 8, n) - 1; it lives in aligned word (sb + b) / 8
+        const uint32_t lastb = (8 * j + 8 < n ? 8 * j + 8 : n) - 1;
+        hi[k] = (j < words && (sb + lastb) / 8 > j) ? ld_sys_u64(s0 + j + 1) : 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kCopyBatch; k++) {
+      const uint32_t j = base + 32 * k + lane;
+      if (j < words) {
+        uint64_t w = sh ? (lo[k] >> sh) | (hi[k] << (64 - sh)) : lo[k];
+        const uint32_t rem = n - 8 * j;
+        if (rem < 8) w &= (1ull << (8 * rem)) - 1;
+        *reinterpret_cast<uint64_t*>(ring + ((off + 8ull * j) & mask)) = w;
+        if (eslot) {  // the same words to the receiver's host slot (eager push), folded into its checksum
+          st_sys_u64(eslot + 8ull * j, w);
+          cs ^= eager_word(w, j);
+        }
+      }
     }
   }
+  return cs;
 }
 
 // n ring bytes starting at offset `off` (any alignment, wraps) to `dst` (any alignment; device or
-// pinned host memory).  With `words_out` the 8-byte words that were stored at aligned positions
-// are also folded into an eager checksum (only used with off, dst 8-byte aligned).
+// pinned host memory).
 __device__ __forceinline__ void warp_copy_from_ring(uint8_t* dst, const uint8_t* ring, uint64_t mask, uint64_t off,
                                                     uint32_t n, uint32_t lane) {
   const uintptr_t d = reinterpret_cast<uintptr_t>(dst);
@@ -1224,14 +1240,25 @@ __device__ __forceinline__ void warp_copy_from_ring(uint8_t* dst, const uint8_t*
   const uint64_t o = off + head;
   const uint32_t sh = (uint32_t)(o & 7) * 8;
   const uint64_t o0 = o & ~7ull;
-  for (uint32_t k = lane; k < nwords; k += 32) {
-    const uint64_t lo = ld_volatile_u64(ring + ((o0 + 8ull * k) & mask));
-    uint64_t w = lo;
-    if (sh) {
-      const uint64_t hi = ld_volatile_u64(ring + ((o0 + 8ull * k + 8) & mask));
-      w = (lo >> sh) | (hi << (64 - sh));
+  for (uint32_t base = 0; base < nwords; base += 32 * kCopyBatch) {
+    uint64_t lo[kCopyBatch], hi[kCopyBatch];
+#pragma unroll
+    for (int k = 0; k < kCopyBatch; k++) {
+      const uint32_t j = base + 32 * k + lane;
+      lo[k] = j < nwords ? ld_volatile_u64(ring + ((o0 + 8ull * j) & mask)) : 0;
     }
-    *reinterpret_cast<uint64_t*>(dst + head + 8ull * k) = w;
+    if (sh) {
+#pragma unroll
+      for (int k = 0; k < kCopyBatch; k++) {
+        const uint32_t j = base + 32 * k + lane;
+        hi[k] = j < nwords ? ld_volatile_u64(ring + ((o0 + 8ull * j + 8) & mask)) : 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kCopyBatch; k++) {
+      const uint32_t j = base + 32 * k + lane;
+      if (j < nwords) *reinterpret_cast<uint64_t*>(dst + head + 8ull * j) = sh ? (lo[k] >> sh) | (hi[k] << (64 - sh)) : lo[k];
+    }
   }
   const uint32_t tail = n - head - 8 * nwords;
   if (lane < tail) dst[head + 8 * nwords + lane] = ld_volatile_u8(ring + ((o + 8ull * nwords + lane) & mask));
@@ -1249,18 +1276,53 @@ __device__ __forceinline__ void warp_zero_ring(uint8_t* ring, uint64_t mask, uin
   if (lane < tail) ring[(o + 8 * nwords + lane) & mask] = 0;
 }
 
-// ---- readiness of pair Q after something changed in its ring / cursors: mirror + eager push -----
-// Called by the owner warp only (Q's small Recv / Retire, or the small Send of Q's loopback peer:
-// all program-ordered in this warp).  The frame at the head, when complete and <= kEagerMax, is
-// copied to Q's host slot first, then the mirror says "has message": a Recv that finds a valid
-// record takes the bytes from the slot and posts an asynchronous Retire instead of waiting for a
-// trip to the GPU and back.
-__device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, PairDev* Q, int qslot, bool full_mirror,
-                                               uint32_t lane) {
-  const uint64_t cap = VL(Q->cap), mask = cap - 1;
-  const uint8_t* ring = VL(Q->ring);
-  const uint64_t head = VL(Q->head), remain = VL(Q->remain);
-  PairMirror* mirror = VL(Q->mirror);
+// Per owner warp: the pair lines of the op being executed, read through with ONE trip to L2 (16-byte
+// system-coherent loads, lanes in parallel) instead of a chain of dependent field loads.
+struct OwnerScratch {
+  PairDev p;     // the op's pair
+  PairDev q;     // its loopback peer (Send only)
+  PairSvc qs;    // service state of the pair whose ring the op changes (peer for Send, own for Recv)
+};
+
+__device__ __forceinline__ void load_lines(OwnerScratch& sc, const SvcParams& sp, int pslot, int qslot, int sslot,
+                                           uint32_t lane) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (lane < 8) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.pairs[pslot]) + lane);
+  else if (lane < 16 && qslot >= 0) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.pairs[qslot]) + (lane - 8));
+  else if (lane == 16 && sslot >= 0) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.psvc[sslot]));
+  if (lane < 8) reinterpret_cast<uint4*>(&sc.p)[lane] = v;
+  else if (lane < 16) reinterpret_cast<uint4*>(&sc.q)[lane - 8] = v;
+  else if (lane == 16) *reinterpret_cast<uint4*>(&sc.qs) = v;
+  __syncwarp();
+}
+
+// the eager record of pair `qslot`: frame of `size` bytes at the head of its ring, pushed while its delivered
+// count is `at`; `cs` = XOR of eager_word() over the payload words (reduced over the warp)
+__device__ __forceinline__ void eager_publish(const SvcParams& sp, int qslot, uint64_t at, uint64_t size, uint64_t cs,
+                                              uint32_t lane) {
+  for (int o = 16; o > 0; o >>= 1) cs ^= __shfl_xor_sync(0xffffffffu, cs, o);
+  cs ^= eager_mix(at * 31 + size);
+  if (lane == 0) {
+    EagerRec* r = &sp.erec[qslot];
+    uint4 a, b;
+    a.x = (uint32_t)at; a.y = (uint32_t)(at >> 32); a.z = (uint32_t)cs; a.w = (uint32_t)(cs >> 32);
+    b.x = (uint32_t)size; b.y = kEagerMagic; b.z = 0; b.w = 0;
+    st_sys_v4(r, a);
+    st_sys_v4(reinterpret_cast<uint8_t*>(r) + 16, b);
+    VL(sp.psvc[qslot].pushed_at) = at;
+  }
+}
+
+// ---- readiness of pair Q (cursor values given) after its own Recv / Retire: mirror + eager push of the
+// next frame.  Called by the owner warp only: everything that touches a connection's small ops is
+// program-ordered in this warp.  The frame at the head, when complete and <= kEagerMax, is copied to Q's
+// host slot first, then the mirror says "has message": a Recv that finds a valid record takes the bytes
+// from the slot and owes a Retire instead of waiting for a trip to the GPU and back.
+__device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, const PairDev& Q, int qslot, uint64_t head,
+                                               uint64_t mh, uint64_t remain, uint64_t acc, uint64_t delivered,
+                                               uint64_t pushed_at, uint32_t lane) {
+  const uint64_t cap = Q.cap, mask = cap - 1;
+  const uint8_t* ring = Q.ring;
   uint32_t hm = 0;
   uint64_t rd = 0;
   if (remain > 0) {
@@ -1270,46 +1332,44 @@ __device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, PairDev* Q, 
     const uint64_t hdr = ld_volatile_u64(ring + head);
     hm = hdr != 0;
     if (hdr != 0 && hdr <= cap - kReserved) {
+      // the footer and (speculatively) the payload words in the same trip
+      const bool small = hdr <= kEagerMax && sp.erec != nullptr && pushed_at != delivered;
+      const uint32_t words = small ? (uint32_t)((hdr + 7) >> 3) : 0;
+      uint64_t w[kEagerMax / 8 / 32];
+#pragma unroll
+      for (int k = 0; k < (int)(kEagerMax / 8 / 32); k++) {
+        const uint32_t j = k * 32 + lane;
+        w[k] = j < words ? ld_volatile_u64(ring + ((head + 8 + 8ull * j) & mask)) : 0;
+      }
       const uint64_t foot = ld_volatile_u64(ring + ((head + 8 + round_up8(hdr)) & mask));
-      if (foot == kFooter) rd = hdr;
-    }
-    PairSvc* S = &sp.psvc[qslot];
-    if (rd != 0 && rd <= kEagerMax && sp.erec != nullptr) {
-      const uint64_t at = VL(S->delivered);
-      if (VL(S->pushed_at) != at) {
-        uint8_t* slot = sp.eslots + (size_t)qslot * kEagerMax;
-        const uint32_t words = (uint32_t)((rd + 7) >> 3);
-        uint64_t cs = 0;
-        for (uint32_t j = lane; j < words; j += 32) {
-          uint64_t w = ld_volatile_u64(ring + ((head + 8 + 8ull * j) & mask));
-          const uint32_t rem = (uint32_t)rd - 8 * j;
-          if (rem < 8) w &= (1ull << (8 * rem)) - 1;
-          st_sys_u64(slot + 8ull * j, w);
-          cs ^= eager_word(w, j);
-        }
-        for (int o = 16; o > 0; o >>= 1) cs ^= __shfl_xor_sync(0xffffffffu, cs, o);
-        cs ^= eager_mix(at * 31 + rd);
-        if (lane == 0) {
-          EagerRec* r = &sp.erec[qslot];
-          uint4 a, b;
-          a.x = (uint32_t)at; a.y = (uint32_t)(at >> 32); a.z = (uint32_t)cs; a.w = (uint32_t)(cs >> 32);
-          b.x = (uint32_t)rd; b.y = kEagerMagic; b.z = 0; b.w = 0;
-          st_sys_v4(r, a);
-          st_sys_v4(reinterpret_cast<uint8_t*>(r) + 16, b);
-          S->pushed_at = at;
+      if (foot == kFooter) {
+        rd = hdr;
+        if (small) {
+          uint8_t* slot = sp.eslots + (size_t)qslot * kEagerMax;
+          uint64_t cs = 0;
+#pragma unroll
+          for (int k = 0; k < (int)(kEagerMax / 8 / 32); k++) {
+            const uint32_t j = k * 32 + lane;
+            if (j < words) {
+              uint64_t x = w[k];
+              const uint32_t rem = (uint32_t)hdr - 8 * j;
+              if (rem < 8) x &= (1ull << (8 * rem)) - 1;
+              st_sys_u64(slot + 8ull * j, x);
+              cs ^= eager_word(x, j);
+            }
+          }
+          eager_publish(sp, qslot, delivered, hdr, cs, lane);
         }
       }
     }
   }
   __syncwarp();
-  if (lane == 0 && mirror) {
-    volatile PairMirror* vm = mirror;
-    if (full_mirror) {
-      vm->head = head;
-      vm->moving_head = VL(Q->moving_head);
-      vm->remain = remain;
-      vm->acc = VL(Q->acc);
-    }
+  if (lane == 0 && Q.mirror) {
+    volatile PairMirror* vm = Q.mirror;
+    vm->head = head;
+    vm->moving_head = mh;
+    vm->remain = remain;
+    vm->acc = acc;
     vm->readable = rd;
     vm->has_message = hm;
   }
@@ -1318,23 +1378,27 @@ __device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, PairDev* Q, 
 // ---- one PairPollable::Send call by one warp (pair.cc:645-734): <= kSvcInline slices, <= kSmallMax bytes.
 // Same planning arithmetic as send_produce_segment (credit snapshot once, prefix scan of encoded sizes,
 // first slice that does not fit is cut to CWS(room), zero-length slice stops the call), then the warp
-// moves the frames itself.
-__device__ __forceinline__ void svc_send_small(const SvcParams& sp, const SvcCmd& c, OpResult& res, uint32_t lane) {
-  PairDev* P = &sp.pairs[c.slot];
+// moves the frames itself.  Memory trips: pair lines (one), payload (one, over PCIe for host slices),
+// then only stores; when the first frame lands at the head of the peer's ring its payload goes to the
+// peer's host slot straight from the words just loaded.
+__device__ __forceinline__ void svc_send_small(const SvcParams& sp, OwnerScratch& sc, const SvcCmd& c, int pslot,
+                                               int peer_hint, OpResult& res, uint32_t lane) {
   res.bytes = 0;
   res.calls = 0;
-  if (VL(P->status) != kStConnected) return;  // pair.cc:657
-  const uint64_t cap = VL(P->cap), mask = cap - 1;
-  uint8_t* ring = VL(P->peer_ring);
-  const bool sys_scope = VL(P->wire) != 0;
-  const uint64_t rt = VL(P->remote_tail);
-  const uint32_t max_sge = VL(P->max_sge);
-  const int peer_slot = VL(P->peer_slot);
-  PairMirror* mirror = VL(P->mirror);
-  const uint64_t rh = sys_scope ? ld_acquire_u64(&P->credit_head) : ld_volatile_u64(&P->credit_head);
+  load_lines(sc, sp, pslot, peer_hint, peer_hint, lane);
+  const PairDev& P = sc.p;
+  if (P.peer_slot != peer_hint) load_lines(sc, sp, pslot, P.peer_slot, P.peer_slot, lane);  // (stale hint)
+  if (P.status != kStConnected) return;  // pair.cc:657
+  const uint64_t cap = P.cap, mask = cap - 1;
+  uint8_t* ring = P.peer_ring;
+  const bool sys_scope = P.wire != 0;
+  const uint64_t rt = P.remote_tail;
+  const uint64_t rh = P.credit_head;  // credit snapshot, once (pair.cc:650); read through with the line
+  const int peer_slot = P.peer_slot;  // -1: no loopback peer
+  if (sys_scope) __threadfence_system();  // remote receiver: its zeroes before its credit, our frames after it
   const uint64_t staging = cap / 2;
   const uint32_t nsl = (uint32_t)c.n;
-  const uint32_t look = (uint32_t)(c.nreal < max_sge ? c.nreal : max_sge);
+  const uint32_t look = (uint32_t)(c.nreal < P.max_sge ? c.nreal : P.max_sge);
   const uint8_t* ptr = nullptr;
   uint64_t len = 0, raw = 0;
   if (lane < nsl) {
@@ -1373,60 +1437,78 @@ __device__ __forceinline__ void svc_send_small(const SvcParams& sp, const SvcCmd
     esum += __shfl_xor_sync(0xffffffffu, esum, o);
   }
   const uint64_t foff = (rt + a) & mask;
+  // eager: the first frame lands exactly at the head of the peer's (empty) ring
+  const uint64_t p0 = __shfl_sync(0xffffffffu, p, 0);
+  const bool at_head = peer_slot >= 0 && nframes > 0 && sc.q.remain == 0 && sc.q.head == rt;
+  const bool eager = at_head && p0 <= kEagerMax && sp.erec != nullptr && sc.qs.pushed_at != sc.qs.delivered;
+  uint8_t* eslot = eager ? sp.eslots + (size_t)peer_slot * kEagerMax : nullptr;
+  uint64_t cs = 0;
   for (uint32_t f = 0; f < nframes; f++) {
     const uint8_t* fsrc = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(ptr), f));
     const uint32_t fp = (uint32_t)__shfl_sync(0xffffffffu, p, f);
     const uint64_t fo = __shfl_sync(0xffffffffu, foff, f);
     if (lane == 0) *reinterpret_cast<uint64_t*>(ring + fo) = fp;  // AppendHeader
-    warp_copy_to_ring(ring, mask, (fo + 8) & mask, fsrc, fp, lane);
+    cs ^= warp_copy_to_ring(ring, mask, (fo + 8) & mask, fsrc, fp, f == 0 ? eslot : nullptr, lane);
   }
-  // footers last (ring_buffer.cc:75-96): everything else of the call is made visible first
+  // footers last (ring_buffer.cc:75-96).  A remote reader (nvlink wire) must see everything else of the call
+  // first: system fence.  On the loopback wire every reader of this ring is ordered behind this warp -- its own
+  // later ops, or a pool / one-shot kernel that starts after a fenced hand-over -- and a fence here would
+  // also wait for the posted PCIe stores of the previous answer: none.
   if (sys_scope) __threadfence_system();
-  else __threadfence();
   __syncwarp();
   if (p != 0) *reinterpret_cast<uint64_t*>(ring + ((foff + 8 + round_up8(p)) & mask)) = kFooter;
-  __syncwarp();
   if (lane == 0) {
-    P->remote_tail = (rt + esum) & mask;
-    P->partial_write = wsum < total;  // pair.cc:712
-    if (mirror) {
-      volatile PairMirror* vm = mirror;
+    PairDev* Pg = &sp.pairs[pslot];
+    VL(Pg->remote_tail) = (rt + esum) & mask;
+    VL(Pg->partial_write) = wsum < total;  // pair.cc:712
+    if (P.mirror) {
+      volatile PairMirror* vm = P.mirror;
       vm->remote_tail = (rt + esum) & mask;
       vm->partial_write = wsum < total;
       vm->credit_head = rh;
-      vm->peer_exit = *(volatile const uint32_t*)&P->credit_exit;
+      vm->peer_exit = P.credit_exit;
     }
   }
   res.bytes = wsum;
   res.calls = wsum ? 1 : 0;
-  __syncwarp();
-  if (peer_slot >= 0 && wsum) {
-    __threadfence();  // the footers before the probe that reads them back
-    svc_rx_refresh(sp, &sp.pairs[peer_slot], peer_slot, false, lane);
+  if (at_head) {
+    // the peer's readiness: it was empty, now the frame at its head is ours (complete: its footer is written)
+    if (eager) eager_publish(sp, peer_slot, sc.qs.delivered, p0, cs, lane);
+    if (lane == 0 && sc.q.mirror) {
+      volatile PairMirror* vm = sc.q.mirror;
+      vm->readable = p0;
+      vm->has_message = 1;
+    }
   }
+  __syncwarp();
 }
 
 // ---- one PairPollable::Recv call by one warp (ring_buffer.cc:122-191 + pair.cc:264-286).  Returns false
 // when the call would move more than kSmallMax bytes (nothing touched: the pool takes it).  With `discard`
-// the payload is not stored anywhere (Retire: the host already took it from the eager slot); every state
-// transition is that of Recv(cap).
-__device__ __forceinline__ bool svc_recv_small(const SvcParams& sp, int slot, uint8_t* dst, uint64_t capacity,
-                                               bool discard, OpResult& res, uint32_t lane) {
-  PairDev* Q = &sp.pairs[slot];
+// the payload is not stored anywhere (Retire: the host already took it from the eager slot, the frame is the
+// whole frame of `capacity` bytes at the head); every state transition is that of Recv(capacity).
+__device__ __forceinline__ bool svc_recv_small(const SvcParams& sp, OwnerScratch& sc, int slot, uint8_t* dst,
+                                               uint64_t capacity, bool discard, OpResult& res, uint32_t lane) {
   res.bytes = 0;
   res.calls = 0;
-  if (VL(Q->status) != kStConnected) return true;  // pair.cc:266-268
-  const uint64_t cap = VL(Q->cap), mask = cap - 1;
-  uint8_t* ring = VL(Q->ring);
-  uint64_t head = VL(Q->head), mh = VL(Q->moving_head), remain = VL(Q->remain), acc = VL(Q->acc);
+  load_lines(sc, sp, slot, -1, slot, lane);
+  const PairDev& Q = sc.p;
+  if (Q.status != kStConnected) return true;  // pair.cc:266-268
+  const uint64_t cap = Q.cap, mask = cap - 1;
+  uint8_t* ring = Q.ring;
+  uint64_t head = Q.head, mh = Q.moving_head, remain = Q.remain, acc = Q.acc;
   uint64_t r, src;
   bool open;
   if (remain > 0) {
     r = remain;
     src = mh;
     open = false;
+  } else if (discard) {  // the frame the host consumed from its slot: pushed from this very position
+    r = capacity;
+    src = (head + 8) & mask;
+    open = true;
   } else {  // GetReadableSize, ring_buffer.cc:67-97
-    const bool sys = VL(Q->wire) != 0;
+    const bool sys = Q.wire != 0;
     const uint64_t hdr = sys ? ld_acquire_u64(ring + head) : ld_volatile_u64(ring + head);
     if (hdr == 0 || hdr > cap - kReserved) return true;
     const uint8_t* fp = ring + ((head + 8 + round_up8(hdr)) & mask);
@@ -1460,31 +1542,34 @@ __device__ __forceinline__ bool svc_recv_small(const SvcParams& sp, int slot, ui
     acc = 0;
   }
   __syncwarp();
-  if (credit) {
-    __threadfence_system();  // the sender may reuse the space only once it reads as zero
-    __syncwarp();
-    if (lane == 0) {
-      st_release_v2u64(VL(Q->peer_credit), mh_after, 0);  // updateStatus, pair.cc:624-641
-      PairMirror* pm = VL(Q->peer_mirror);
-      if (pm) ((volatile PairMirror*)pm)->credit_head = mh_after;
+  if (credit) {  // updateStatus, pair.cc:624-641: the 16-byte status_report
+    if (Q.wire != 0) {
+      __threadfence_system();  // a remote sender may reuse the space only once it reads as zero
+      __syncwarp();
+      if (lane == 0) st_release_v2u64(Q.peer_credit, mh_after, 0);
+    } else if (lane == 0) {  // loopback: the sender is ordered behind this warp (see svc_send_small)
+      asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(Q.peer_credit), "l"(mh_after), "l"(0ull) : "memory");
     }
+    if (lane == 0 && Q.peer_mirror) ((volatile PairMirror*)Q.peer_mirror)->credit_head = mh_after;
   }
+  const uint64_t delivered = sc.qs.delivered + n;
   if (lane == 0) {
-    Q->head = head;
-    Q->moving_head = mh_after;
-    Q->remain = remain;
-    Q->acc = acc;
-    VL(sp.psvc[slot].delivered) = VL(sp.psvc[slot].delivered) + n;
+    PairDev* Qg = &sp.pairs[slot];
+    VL(Qg->head) = head;
+    VL(Qg->moving_head) = mh_after;
+    VL(Qg->remain) = remain;
+    VL(Qg->acc) = acc;
+    VL(sp.psvc[slot].delivered) = delivered;
   }
-  __syncwarp();
-  __threadfence();
+  __syncwarp();  // (the zeroes are ordered before anything this warp does next; see svc_send_small)
   res.bytes = n;
   res.calls = 1;
-  svc_rx_refresh(sp, Q, slot, true, lane);
+  svc_rx_refresh(sp, Q, slot, head, mh_after, remain, acc, delivered, sc.qs.pushed_at, lane);
   return true;
 }
 
 struct OwnerShared {  // per owner warp
+  OwnerScratch sc;
   SvcCmd cmd[2];
   int32_t box_a[kOwnBoxes], box_b[kOwnBoxes];  // pair slot of a job in flight (-1: box free) and its loopback peer
   uint32_t box_kind[kOwnBoxes];
@@ -1563,8 +1648,8 @@ __global__ void __launch_bounds__(128) k_svc_owner(SvcParams sp) {
     res.calls = 0;
     bool answer = true;
     if (opc != kSvcNop) {
-      PairDev* P = &sp.pairs[c.slot];
-      const int peer = VL(P->peer_slot);
+      // the host packs the loopback peer's slot next to the pair's own (saves a dependent load)
+      const int pslot = c.slot & 0xffff, peer = (c.slot >> 16) - 1;
       bool small = false;
       if (opc == kSvcSend) {
         uint64_t bytes = 0;
@@ -1576,13 +1661,25 @@ __global__ void __launch_bounds__(128) k_svc_owner(SvcParams sp) {
         small = !(c.flags & kFlagUntilBlocked);
       }
       bool done_small = false;
+      // a Retire the host owes for this same pair rides on its next Send (flags >> 16 = frame size).  The two
+      // commute (Retire touches the pair's receive side and the peer's credit, Send neither), so a small Send
+      // goes first -- its bytes are what the peer is waiting for.
+      const uint32_t owed = opc == kSvcSend ? c.flags >> 16 : 0;
+      if (small || owed) owner_reap(sp, boxes, os, pslot, peer, lane);  // nothing of this connection may be in flight in the pool
+      if (owed && !small) {
+        OpResult r2;
+        svc_recv_small(sp, os.sc, pslot, nullptr, owed, true, r2, lane);
+      }
       if (small) {
-        owner_reap(sp, boxes, os, c.slot, peer, lane);  // nothing of this connection may be in flight in the pool
         if (opc == kSvcSend) {
-          svc_send_small(sp, c, res, lane);
+          svc_send_small(sp, os.sc, c, pslot, peer, res, lane);
           done_small = true;
+          if (owed) {
+            OpResult r2;
+            svc_recv_small(sp, os.sc, pslot, nullptr, owed, true, r2, lane);
+          }
         } else {
-          done_small = svc_recv_small(sp, c.slot, reinterpret_cast<uint8_t*>(c.ptr), c.n, opc == kSvcRetire, res, lane);
+          done_small = svc_recv_small(sp, os.sc, pslot, reinterpret_cast<uint8_t*>(c.ptr), c.n, opc == kSvcRetire, res, lane);
         }
       }
       if (!done_small) {
@@ -1601,15 +1698,15 @@ __global__ void __launch_bounds__(128) k_svc_owner(SvcParams sp) {
         BigBox* bx = &boxes[bi];
         if (lane == 0) {
           bx->kind = opc == kSvcSend ? kSvcSend : kSvcRecv;
-          bx->slot = c.slot;
-          bx->flags = c.flags | kFlagConcurrent;  // the two ends' jobs run side by side in the pool
+          bx->slot = pslot;
+          bx->flags = (c.flags & 0xffffu) | kFlagConcurrent;  // the two ends' jobs run side by side in the pool
           bx->ptr = c.ptr;
           bx->n = c.n;
           bx->byte_idx = c.byte_idx;
           bx->nreal = c.nreal;
           bx->done = &qdone[(expect - 1) % kOwnQ];
           bx->seq = expect;
-          os.box_a[bi] = c.slot;
+          os.box_a[bi] = pslot;
           os.box_b[bi] = peer;
           os.box_kind[bi] = opc == kSvcSend ? kSvcSend : kSvcRecv;
         }

@@ -103,6 +103,8 @@ struct b200_pair {
   std::atomic<bool> retire_pending{false};
   int retire_q = 0;
   uint64_t retire_ticket = 0;
+  std::atomic<uint32_t> retire_owed{0};  // size of an eagerly received frame whose Retire has not been posted yet:
+                                         // it rides on the pair's next Send, or is posted by whoever looks next
 };
 
 constexpr int kLanes = 16;  // max internal lanes of the host-staged path (B200_LANES, default 8)
@@ -1091,9 +1093,27 @@ static bool svc_wait(Runtime& r, int q, uint64_t t, uint64_t* bytes, uint64_t* c
 
 // the asynchronous Retire of the last eagerly received frame must have run before anything looks at the
 // pair's receive side again (mirror, state, ring image) -- it is a couple of microseconds behind at most
+static int owner_of(const Runtime& r, const b200_pair* p);
+static int32_t slot_word(const b200_pair* p) {  // SvcCmd.slot: the pair's slot, the loopback peer's slot + 1 above it
+  return (int32_t)((uint32_t)p->slot | (p->peer_local ? ((uint32_t)p->peer_local->slot + 1) << 16 : 0));
+}
 static void drain_retire(b200_pair* p) {
-  if (!p->retire_pending.load(std::memory_order_acquire)) return;
   Runtime& r = R();
+  const uint32_t owed = p->retire_owed.exchange(0, std::memory_order_acq_rel);
+  if (owed && r.svc_running.load()) {
+    const int q = owner_of(r, p);
+    p->retire_q = q;
+    p->retire_ticket = svc_post(r, q, [&](SvcCmd* c, SliceDev*) {
+      c->op = kSvcRetire;
+      c->slot = slot_word(p);
+      c->flags = B200_BATCH_ONE_CALL;
+      c->ptr = 0;
+      c->n = owed;
+      c->byte_idx = 0;
+    });
+    p->retire_pending.store(true, std::memory_order_release);
+  }
+  if (!p->retire_pending.load(std::memory_order_acquire)) return;
   if (r.svc_running.load()) svc_wait(r, p->retire_q, p->retire_ticket, nullptr, nullptr);
   p->retire_pending.store(false, std::memory_order_release);
 }
@@ -1173,7 +1193,7 @@ extern "C" uint64_t b200_service_eager_hits(void) { return R().svc_eager_hits.lo
 static bool svc_fill_send(b200_pair* p, SvcCmd* c, SliceDev* area, const b200_slice* slices, size_t n, size_t byte_idx,
                           uint32_t flags) {
   size_t look = n;
-  if (!(flags & B200_BATCH_UNTIL_BLOCKED) && look > (size_t)p->max_sge) look = (size_t)p->max_sge;
+  if (!(flags & B200_BATCH_UNTIL_BLOCKED) && look > (size_t)p->max_sge) look = (size_t)p->max_sge;  // (flags >> 16: owed Retire)
   if (look > kSvcSliceArea - 1) look = kSvcSliceArea - 1;
   uint64_t rest = 0;
   for (size_t i = look; i < n; i++) rest += slices[i].len;
@@ -1204,7 +1224,7 @@ static bool svc_fill_send(b200_pair* p, SvcCmd* c, SliceDev* area, const b200_sl
     out[look].len = rest;
   }
   c->op = kSvcSend;
-  c->slot = p->slot;
+  c->slot = slot_word(p);
   c->flags = flags;
   c->ptr = (uint64_t)(uintptr_t)area;
   c->n = nsl;
@@ -1216,9 +1236,16 @@ static bool svc_fill_send(b200_pair* p, SvcCmd* c, SliceDev* area, const b200_sl
 static uint64_t svc_send(Runtime& r, b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
   const int q = owner_of(r, p);
   bool ok = true;
+  // the Retire of an eagerly received frame rides on this Send (executed right after it by the owner warp)
+  const uint32_t owed = p->retire_owed.exchange(0, std::memory_order_acq_rel);
   const uint64_t t = svc_post(r, q, [&](SvcCmd* c, SliceDev* area) {
-    ok = svc_fill_send(p, c, area, slices, n, byte_idx, B200_BATCH_ONE_CALL);
-    if (!ok) c->op = kSvcNop;
+    ok = svc_fill_send(p, c, area, slices, n, byte_idx, B200_BATCH_ONE_CALL | (owed << 16));
+    if (!ok) {
+      c->op = owed ? kSvcRetire : kSvcNop;
+      c->slot = slot_word(p);
+      c->flags = B200_BATCH_ONE_CALL;
+      c->n = owed;
+    }
   });
   uint64_t bytes = 0;
   if (!svc_wait(r, q, t, &bytes, nullptr) || !ok) {
@@ -1257,16 +1284,7 @@ static uint64_t svc_recv(Runtime& r, b200_pair* p, void* dst, uint64_t cap) {
       memcpy(dst, slot, size);
       if (eager_checksum((const uint8_t*)dst, size, at) != cs) continue;  // payload stores still in flight: look again
       p->svc_delivered += size;
-      p->retire_q = q;
-      p->retire_ticket = svc_post(r, q, [&](SvcCmd* c, SliceDev*) {
-        c->op = kSvcRetire;
-        c->slot = p->slot;
-        c->flags = B200_BATCH_ONE_CALL;
-        c->ptr = 0;
-        c->n = size;
-        c->byte_idx = 0;
-      });
-      p->retire_pending.store(true, std::memory_order_release);
+      p->retire_owed.store(size, std::memory_order_release);  // rides on the next Send, or drain_retire posts it
       r.svc_eager_hits++;
       return size;
     }
@@ -1281,7 +1299,7 @@ static uint64_t svc_recv(Runtime& r, b200_pair* p, void* dst, uint64_t cap) {
   }
   const uint64_t t = svc_post(r, q, [&](SvcCmd* c, SliceDev*) {
     c->op = kSvcRecv;
-    c->slot = p->slot;
+    c->slot = slot_word(p);
     c->flags = B200_BATCH_ONE_CALL;
     c->ptr = (uint64_t)(uintptr_t)kdst;
     c->n = kcap;
@@ -1835,6 +1853,12 @@ static void poller_service_pass(Runtime& r, const std::vector<b200_pair*>& snap)
   if (n) r.svc_ready_seen += n;
   for (b200_pair* p : snap) {
     if (!r.svc_level[p->slot]) continue;
+    if (p->retire_owed.load(std::memory_order_acquire)) {
+      // the frame the device still reports was already taken from the eager slot: post its Retire now
+      // (nobody sent on the pair since) instead of waking the engine for it
+      drain_retire(p);
+      continue;
+    }
     struct pollfd pfd = {p->wakeup_fd, POLLIN, 0};
     if (poll(&pfd, 1, 0) <= 0) kick(p);
   }

@@ -10,6 +10,8 @@
 // running (b200_service_start) no call launches anything.
 #include <pthread.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -30,6 +32,7 @@ struct Worker {
   pthread_barrier_t* bar;
   std::atomic<int>* stop;
   int err;
+  uint64_t t_send = 0, t_wait = 0, t_recv = 0, n_ops = 0;  // phase times (ns), B200_PP_TRACE
 };
 
 inline uint64_t now_ns() {
@@ -48,12 +51,17 @@ void* run(void* arg) {
       for (int c = 0; c < w->n; c++) {
         b200_pair* p = w->srv[w->first + c];
         if (!b200_pair_has_message(p)) continue;
+        const uint64_t s0 = now_ns();
         got[c] += b200_pair_recv(p, w->buf + w->msg + got[c], w->msg - got[c]);
+        const uint64_t s1 = now_ns();
+        w->t_recv += s1 - s0;
         if (got[c] == w->msg) {
           got[c] = 0;
           b200_slice sl{w->buf + w->msg, w->msg};
           uint64_t sent = 0;
           while (sent < w->msg && !w->stop->load(std::memory_order_relaxed)) sent += b200_pair_send(p, &sl, 1, sent);
+          w->t_send += now_ns() - s1;
+          w->n_ops++;
         }
       }
     }
@@ -66,17 +74,28 @@ void* run(void* arg) {
         b200_slice sl{w->buf, w->msg};
         uint64_t sent = 0;
         while (sent < w->msg) sent += b200_pair_send(p, &sl, 1, sent);
-        uint64_t got = 0;
+        const uint64_t t1 = now_ns();
+        uint64_t got = 0, twait = 0, trecv = 0;
         while (got < w->msg) {
+          const uint64_t a0 = now_ns();
           while (!b200_pair_has_message(p)) {
             if (now_ns() - t0 > 20000000000ull) {
               w->err = 1;
               return nullptr;
             }
           }
+          const uint64_t a1 = now_ns();
           got += b200_pair_recv(p, w->buf + w->msg + got, w->msg - got);
+          twait += a1 - a0;
+          trecv += now_ns() - a1;
         }
-        if (k >= 0) w->rtt_ns[(size_t)(w->first + c) * w->iters + k] = now_ns() - t0;
+        if (k >= 0) {
+          w->rtt_ns[(size_t)(w->first + c) * w->iters + k] = now_ns() - t0;
+          w->t_send += t1 - t0;
+          w->t_wait += twait;
+          w->t_recv += trecv;
+          w->n_ops++;
+        }
         if (memcmp(w->buf, w->buf + w->msg, w->msg) != 0) w->err = 2;  // echo must be bit-exact
       }
     }
@@ -128,6 +147,16 @@ extern "C" double b200_pp_run(int conns, int groups, int iters, int warm, uint64
   pthread_barrier_destroy(&bar);
   int err = 0;
   for (auto& w : ws) err |= w.err;
+  if (getenv("B200_PP_TRACE")) {
+    uint64_t cs = 0, cw = 0, cr = 0, cn = 0, ss = 0, sr = 0, sn = 0;
+    for (auto& w : ws) {
+      if (w.is_server) { ss += w.t_send; sr += w.t_recv; sn += w.n_ops; }
+      else { cs += w.t_send; cw += w.t_wait; cr += w.t_recv; cn += w.n_ops; }
+    }
+    if (cn && sn)
+      fprintf(stderr, "pp trace conns=%d: client send %.2f us, wait-for-echo %.2f us, recv %.2f us | server recv %.2f us, send %.2f us\n",
+              conns, cs / 1e3 / cn, cw / 1e3 / cn, cr / 1e3 / cn, sr / 1e3 / sn, ss / 1e3 / sn);
+  }
   for (int c = 0; c < conns; c++) {
     b200_pair_disconnect(cli[c]);
     b200_pair_disconnect(srv[c]);
