@@ -231,6 +231,7 @@ void launch_poll_scan(PairDev* pairs, const int32_t* slots, uint32_t* events, ui
 
 // owners / pool / poller on three streams; returns false when the resident grids cannot be co-resident
 bool launch_service(const SvcParams& sp, void* s_owner, void* s_big, void* s_poll);
+int svc_trace_read(unsigned long long* out16);  // -DB200_SVC_TRACE builds only (device-side phase timers)
 
 void launch_probe_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes_per_cta, uint64_t stride, int nctas,
                        int threads, uint32_t mis, uint32_t item_bytes, uint32_t dynamic, void* stream);

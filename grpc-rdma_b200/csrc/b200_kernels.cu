@@ -1178,6 +1178,18 @@ __device__ __forceinline__ void st_sys_u64(void* p, uint64_t v) {
 }
 __device__ __forceinline__ uint8_t ld_volatile_u8(const void* p) { return *(const volatile uint8_t*)p; }
 
+#ifdef B200_SVC_TRACE
+__device__ unsigned long long g_svc_trace[16];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE_MARK(i, t0) do { if (lane == 0) atomicAdd(&g_svc_trace[i], gtime() - (t0)); } while (0)
+#else
+#define TRACE_MARK(i, t0) do { } while (0)
+#endif
+
 // ---- warp-level byte movers of the small paths (no shared memory, no barrier) ----------------
 
 // n bytes from `src` (any alignment; device or pinned host memory: system-coherent loads that bypass
@@ -1276,30 +1288,93 @@ __device__ __forceinline__ void warp_zero_ring(uint8_t* ring, uint64_t mask, uin
   if (lane < tail) ring[(o + 8 * nwords + lane) & mask] = 0;
 }
 
-// Per owner warp: the pair lines of the op being executed, read through with ONE trip to L2 (16-byte
-// system-coherent loads, lanes in parallel) instead of a chain of dependent field loads.
-struct OwnerScratch {
-  PairDev p;     // the op's pair
-  PairDev q;     // its loopback peer (Send only)
-  PairSvc qs;    // service state of the pair whose ring the op changes (peer for Send, own for Recv)
+// Per owner warp: a small cache of the connections it serves -- both pairs' lines and service state in
+// shared memory.  Everything that changes a cached line is either this warp itself (small ops: it updates
+// the cached copy and writes through), a pool job (the entry is dropped when the job is handed over) or
+// the host (Init / Connect / Disconnect and kernels launched beside the service: the host bumps a generation
+// that every command carries; a new generation drops the whole cache).  A hit costs no trip to memory at
+// all; a miss reads both lines with one trip (16-byte system-coherent loads, lanes in parallel).  Pairs on
+// the nvlink wire are never kept: their ring and credit word are written from another GPU.
+constexpr int kConnCache = 8;
+struct ConnEntry {
+  PairDev line[2];   // [0] = the pair with the smaller slot ... no order implied: line[i] belongs to slot[i]
+  PairSvc svc[2];
+  int32_t slot[2];   // slot[1] = -1: no loopback peer
+};
+struct ConnView {    // what an op works on
+  PairDev* P;        // the op's pair (cached copy)
+  PairDev* Q;        // its loopback peer or nullptr
+  PairSvc* SP;
+  PairSvc* SQ;
 };
 
-__device__ __forceinline__ void load_lines(OwnerScratch& sc, const SvcParams& sp, int pslot, int qslot, int sslot,
-                                           uint32_t lane) {
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (lane < 8) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.pairs[pslot]) + lane);
-  else if (lane < 16 && qslot >= 0) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.pairs[qslot]) + (lane - 8));
-  else if (lane == 16 && sslot >= 0) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.psvc[sslot]));
-  if (lane < 8) reinterpret_cast<uint4*>(&sc.p)[lane] = v;
-  else if (lane < 16) reinterpret_cast<uint4*>(&sc.q)[lane - 8] = v;
-  else if (lane == 16) *reinterpret_cast<uint4*>(&sc.qs) = v;
+__device__ __forceinline__ ConnView conn_get(ConnEntry* cc, uint32_t& cc_next, const SvcParams& sp, int pslot,
+                                             int peer_hint, uint32_t lane) {
+  int hit = -1, side = 0;
+  {
+    bool mine = false;
+    int myside = 0;
+    if (lane < kConnCache) {
+      if (cc[lane].slot[0] == pslot) mine = true, myside = 0;
+      else if (cc[lane].slot[1] == pslot) mine = true, myside = 1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m) {
+      hit = __ffs(m) - 1;
+      side = __shfl_sync(0xffffffffu, myside, hit);
+    }
+  }
+  if (hit < 0) {
+    hit = (int)(cc_next % kConnCache);
+    cc_next++;
+    side = 0;
+    ConnEntry& e = cc[hit];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (lane < 8) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.pairs[pslot]) + lane);
+    else if (lane < 16 && peer_hint >= 0) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.pairs[peer_hint]) + (lane - 8));
+    else if (lane == 16) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.psvc[pslot]));
+    else if (lane == 17 && peer_hint >= 0) v = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.psvc[peer_hint]));
+    if (lane < 8) reinterpret_cast<uint4*>(&e.line[0])[lane] = v;
+    else if (lane < 16) reinterpret_cast<uint4*>(&e.line[1])[lane - 8] = v;
+    else if (lane == 16) *reinterpret_cast<uint4*>(&e.svc[0]) = v;
+    else if (lane == 17) *reinterpret_cast<uint4*>(&e.svc[1]) = v;
+    __syncwarp();
+    int peer = e.line[0].peer_slot;
+    if (peer != peer_hint) {  // (stale hint from the host: read the right peer)
+      if (lane < 8 && peer >= 0) reinterpret_cast<uint4*>(&e.line[1])[lane] = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.pairs[peer]) + lane);
+      if (lane == 8 && peer >= 0) *reinterpret_cast<uint4*>(&e.svc[1]) = ld_sys_v4(reinterpret_cast<const uint4*>(&sp.psvc[peer]));
+      __syncwarp();
+    }
+    if (lane == 0) {
+      e.slot[0] = pslot;
+      e.slot[1] = peer;
+    }
+    __syncwarp();
+  }
+  ConnEntry& e = cc[hit];
+  ConnView v;
+  v.P = &e.line[side];
+  v.SP = &e.svc[side];
+  const bool has_q = e.slot[side ^ 1] >= 0 && e.slot[side ^ 1] == e.line[side].peer_slot;
+  v.Q = has_q ? &e.line[side ^ 1] : nullptr;
+  v.SQ = has_q ? &e.svc[side ^ 1] : nullptr;
+  return v;
+}
+
+// forget the connection of `pslot` (a pool job or a remote GPU is about to change its lines)
+__device__ __forceinline__ void conn_drop(ConnEntry* cc, int pslot, uint32_t lane) {
+  if (lane < kConnCache && (cc[lane].slot[0] == pslot || cc[lane].slot[1] == pslot)) cc[lane].slot[0] = cc[lane].slot[1] = -1;
+  __syncwarp();
+}
+__device__ __forceinline__ void conn_drop_all(ConnEntry* cc, uint32_t lane) {
+  if (lane < kConnCache) cc[lane].slot[0] = cc[lane].slot[1] = -1;
   __syncwarp();
 }
 
 // the eager record of pair `qslot`: frame of `size` bytes at the head of its ring, pushed while its delivered
 // count is `at`; `cs` = XOR of eager_word() over the payload words (reduced over the warp)
-__device__ __forceinline__ void eager_publish(const SvcParams& sp, int qslot, uint64_t at, uint64_t size, uint64_t cs,
-                                              uint32_t lane) {
+__device__ __forceinline__ void eager_publish(const SvcParams& sp, int qslot, PairSvc* SQ, uint64_t at, uint64_t size,
+                                              uint64_t cs, uint32_t lane) {
   for (int o = 16; o > 0; o >>= 1) cs ^= __shfl_xor_sync(0xffffffffu, cs, o);
   cs ^= eager_mix(at * 31 + size);
   if (lane == 0) {
@@ -1309,6 +1384,7 @@ __device__ __forceinline__ void eager_publish(const SvcParams& sp, int qslot, ui
     b.x = (uint32_t)size; b.y = kEagerMagic; b.z = 0; b.w = 0;
     st_sys_v4(r, a);
     st_sys_v4(reinterpret_cast<uint8_t*>(r) + 16, b);
+    SQ->pushed_at = at;
     VL(sp.psvc[qslot].pushed_at) = at;
   }
 }
@@ -1318,17 +1394,18 @@ __device__ __forceinline__ void eager_publish(const SvcParams& sp, int qslot, ui
 // program-ordered in this warp.  The frame at the head, when complete and <= kEagerMax, is copied to Q's
 // host slot first, then the mirror says "has message": a Recv that finds a valid record takes the bytes
 // from the slot and owes a Retire instead of waiting for a trip to the GPU and back.
-__device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, const PairDev& Q, int qslot, uint64_t head,
-                                               uint64_t mh, uint64_t remain, uint64_t acc, uint64_t delivered,
-                                               uint64_t pushed_at, uint32_t lane) {
+__device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, const PairDev& Q, int qslot, PairSvc* SQ,
+                                               uint64_t head, uint64_t mh, uint64_t remain, uint64_t acc,
+                                               bool known_empty, uint32_t lane) {
   const uint64_t cap = Q.cap, mask = cap - 1;
   const uint8_t* ring = Q.ring;
+  const uint64_t delivered = SQ->delivered, pushed_at = SQ->pushed_at;
   uint32_t hm = 0;
   uint64_t rd = 0;
   if (remain > 0) {
     hm = 1;
     rd = remain;
-  } else {
+  } else if (!known_empty) {
     const uint64_t hdr = ld_volatile_u64(ring + head);
     hm = hdr != 0;
     if (hdr != 0 && hdr <= cap - kReserved) {
@@ -1358,7 +1435,7 @@ __device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, const PairDe
               cs ^= eager_word(x, j);
             }
           }
-          eager_publish(sp, qslot, delivered, hdr, cs, lane);
+          eager_publish(sp, qslot, SQ, delivered, hdr, cs, lane);
         }
       }
     }
@@ -1381,20 +1458,21 @@ __device__ __forceinline__ void svc_rx_refresh(const SvcParams& sp, const PairDe
 // moves the frames itself.  Memory trips: pair lines (one), payload (one, over PCIe for host slices),
 // then only stores; when the first frame lands at the head of the peer's ring its payload goes to the
 // peer's host slot straight from the words just loaded.
-__device__ __forceinline__ void svc_send_small(const SvcParams& sp, OwnerScratch& sc, const SvcCmd& c, int pslot,
-                                               int peer_hint, OpResult& res, uint32_t lane) {
+__device__ __forceinline__ void svc_send_small(const SvcParams& sp, const ConnView& cv, const SvcCmd& c, int pslot,
+                                               OpResult& res, uint32_t lane) {
   res.bytes = 0;
   res.calls = 0;
-  load_lines(sc, sp, pslot, peer_hint, peer_hint, lane);
-  const PairDev& P = sc.p;
-  if (P.peer_slot != peer_hint) load_lines(sc, sp, pslot, P.peer_slot, P.peer_slot, lane);  // (stale hint)
+  PairDev& P = *cv.P;
+#ifdef B200_SVC_TRACE
+  const unsigned long long ts0 = gtime();
+#endif
   if (P.status != kStConnected) return;  // pair.cc:657
   const uint64_t cap = P.cap, mask = cap - 1;
   uint8_t* ring = P.peer_ring;
   const bool sys_scope = P.wire != 0;
   const uint64_t rt = P.remote_tail;
-  const uint64_t rh = P.credit_head;  // credit snapshot, once (pair.cc:650); read through with the line
-  const int peer_slot = P.peer_slot;  // -1: no loopback peer
+  const uint64_t rh = P.credit_head;  // credit snapshot, once (pair.cc:650)
+  const int peer_slot = cv.Q ? P.peer_slot : -1;  // -1: no loopback peer
   if (sys_scope) __threadfence_system();  // remote receiver: its zeroes before its credit, our frames after it
   const uint64_t staging = cap / 2;
   const uint32_t nsl = (uint32_t)c.n;
@@ -1439,8 +1517,8 @@ __device__ __forceinline__ void svc_send_small(const SvcParams& sp, OwnerScratch
   const uint64_t foff = (rt + a) & mask;
   // eager: the first frame lands exactly at the head of the peer's (empty) ring
   const uint64_t p0 = __shfl_sync(0xffffffffu, p, 0);
-  const bool at_head = peer_slot >= 0 && nframes > 0 && sc.q.remain == 0 && sc.q.head == rt;
-  const bool eager = at_head && p0 <= kEagerMax && sp.erec != nullptr && sc.qs.pushed_at != sc.qs.delivered;
+  const bool at_head = peer_slot >= 0 && nframes > 0 && cv.Q->remain == 0 && cv.Q->head == rt;
+  const bool eager = at_head && p0 <= kEagerMax && sp.erec != nullptr && cv.SQ->pushed_at != cv.SQ->delivered;
   uint8_t* eslot = eager ? sp.eslots + (size_t)peer_slot * kEagerMax : nullptr;
   uint64_t cs = 0;
   for (uint32_t f = 0; f < nframes; f++) {
@@ -1450,6 +1528,7 @@ __device__ __forceinline__ void svc_send_small(const SvcParams& sp, OwnerScratch
     if (lane == 0) *reinterpret_cast<uint64_t*>(ring + fo) = fp;  // AppendHeader
     cs ^= warp_copy_to_ring(ring, mask, (fo + 8) & mask, fsrc, fp, f == 0 ? eslot : nullptr, lane);
   }
+  TRACE_MARK(5, ts0);  // after the pair lines: plan + payload loads + ring stores
   // footers last (ring_buffer.cc:75-96).  A remote reader (nvlink wire) must see everything else of the call
   // first: system fence.  On the loopback wire every reader of this ring is ordered behind this warp -- its own
   // later ops, or a pool / one-shot kernel that starts after a fenced hand-over -- and a fence here would
@@ -1459,6 +1538,8 @@ __device__ __forceinline__ void svc_send_small(const SvcParams& sp, OwnerScratch
   if (p != 0) *reinterpret_cast<uint64_t*>(ring + ((foff + 8 + round_up8(p)) & mask)) = kFooter;
   if (lane == 0) {
     PairDev* Pg = &sp.pairs[pslot];
+    P.remote_tail = (rt + esum) & mask;
+    P.partial_write = wsum < total;
     VL(Pg->remote_tail) = (rt + esum) & mask;
     VL(Pg->partial_write) = wsum < total;  // pair.cc:712
     if (P.mirror) {
@@ -1473,9 +1554,9 @@ __device__ __forceinline__ void svc_send_small(const SvcParams& sp, OwnerScratch
   res.calls = wsum ? 1 : 0;
   if (at_head) {
     // the peer's readiness: it was empty, now the frame at its head is ours (complete: its footer is written)
-    if (eager) eager_publish(sp, peer_slot, sc.qs.delivered, p0, cs, lane);
-    if (lane == 0 && sc.q.mirror) {
-      volatile PairMirror* vm = sc.q.mirror;
+    if (eager) eager_publish(sp, peer_slot, cv.SQ, cv.SQ->delivered, p0, cs, lane);
+    if (lane == 0 && cv.Q->mirror) {
+      volatile PairMirror* vm = cv.Q->mirror;
       vm->readable = p0;
       vm->has_message = 1;
     }
@@ -1487,12 +1568,11 @@ __device__ __forceinline__ void svc_send_small(const SvcParams& sp, OwnerScratch
 // when the call would move more than kSmallMax bytes (nothing touched: the pool takes it).  With `discard`
 // the payload is not stored anywhere (Retire: the host already took it from the eager slot, the frame is the
 // whole frame of `capacity` bytes at the head); every state transition is that of Recv(capacity).
-__device__ __forceinline__ bool svc_recv_small(const SvcParams& sp, OwnerScratch& sc, int slot, uint8_t* dst,
+__device__ __forceinline__ bool svc_recv_small(const SvcParams& sp, const ConnView& cv, int slot, uint8_t* dst,
                                                uint64_t capacity, bool discard, OpResult& res, uint32_t lane) {
   res.bytes = 0;
   res.calls = 0;
-  load_lines(sc, sp, slot, -1, slot, lane);
-  const PairDev& Q = sc.p;
+  PairDev& Q = *cv.P;
   if (Q.status != kStConnected) return true;  // pair.cc:266-268
   const uint64_t cap = Q.cap, mask = cap - 1;
   uint8_t* ring = Q.ring;
@@ -1551,10 +1631,16 @@ __device__ __forceinline__ bool svc_recv_small(const SvcParams& sp, OwnerScratch
       asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(Q.peer_credit), "l"(mh_after), "l"(0ull) : "memory");
     }
     if (lane == 0 && Q.peer_mirror) ((volatile PairMirror*)Q.peer_mirror)->credit_head = mh_after;
+    if (lane == 0 && cv.Q) cv.Q->credit_head = mh_after;  // the cached line of the sender
   }
-  const uint64_t delivered = sc.qs.delivered + n;
+  const uint64_t delivered = cv.SP->delivered + n;
   if (lane == 0) {
     PairDev* Qg = &sp.pairs[slot];
+    Q.head = head;
+    Q.moving_head = mh_after;
+    Q.remain = remain;
+    Q.acc = acc;
+    cv.SP->delivered = delivered;
     VL(Qg->head) = head;
     VL(Qg->moving_head) = mh_after;
     VL(Qg->remain) = remain;
@@ -1564,12 +1650,14 @@ __device__ __forceinline__ bool svc_recv_small(const SvcParams& sp, OwnerScratch
   __syncwarp();  // (the zeroes are ordered before anything this warp does next; see svc_send_small)
   res.bytes = n;
   res.calls = 1;
-  svc_rx_refresh(sp, Q, slot, head, mh_after, remain, acc, delivered, sc.qs.pushed_at, lane);
+  // the ring is known to be empty when the new head has reached the loopback sender's tail: no probe needed
+  const bool known_empty = remain == 0 && cv.Q != nullptr && cv.Q->remote_tail == head;
+  svc_rx_refresh(sp, Q, slot, cv.SP, head, mh_after, remain, acc, known_empty, lane);
   return true;
 }
 
 struct OwnerShared {  // per owner warp
-  OwnerScratch sc;
+  ConnEntry cc[kConnCache];
   SvcCmd cmd[2];
   int32_t box_a[kOwnBoxes], box_b[kOwnBoxes];  // pair slot of a job in flight (-1: box free) and its loopback peer
   uint32_t box_kind[kOwnBoxes];
@@ -1607,8 +1695,8 @@ __global__ void __launch_bounds__(128) k_svc_owner(SvcParams sp) {
   SvcDone* qdone = sp.done + (size_t)q * kOwnQ;
   BigBox* boxes = sp.boxes + (size_t)q * kOwnBoxes;
   if (lane < kOwnBoxes) os.box_a[lane] = os.box_b[lane] = -1;
-  __syncwarp();
-  uint32_t expect = 1, avail = 0, cur = 0, idle = 0;
+  conn_drop_all(os.cc, lane);
+  uint32_t expect = 1, avail = 0, cur = 0, idle = 0, cc_next = 0, gen = 0;
   while (true) {
     // ---- fetch: entries `expect` and `expect + 1` in one trip (16 lanes x 16 bytes); both halves of a
     // line carry the stamp because the two 64-byte halves may be read by separate PCIe reads
@@ -1641,8 +1729,15 @@ __global__ void __launch_bounds__(128) k_svc_owner(SvcParams sp) {
       }
     }
     const SvcCmd& c = os.cmd[cur];
-    const uint32_t opc = c.op;
+    const uint32_t opc = c.op & 0xffu;
     if (opc == kSvcStop) break;
+    if ((c.op >> 8) != gen) {  // the host changed pair lines (or launched kernels beside us) since the last command
+      gen = c.op >> 8;
+      conn_drop_all(os.cc, lane);
+    }
+#ifdef B200_SVC_TRACE
+    const unsigned long long tr0 = gtime();
+#endif
     OpResult res;
     res.bytes = 0;
     res.calls = 0;
@@ -1666,24 +1761,34 @@ __global__ void __launch_bounds__(128) k_svc_owner(SvcParams sp) {
       // goes first -- its bytes are what the peer is waiting for.
       const uint32_t owed = opc == kSvcSend ? c.flags >> 16 : 0;
       if (small || owed) owner_reap(sp, boxes, os, pslot, peer, lane);  // nothing of this connection may be in flight in the pool
-      if (owed && !small) {
-        OpResult r2;
-        svc_recv_small(sp, os.sc, pslot, nullptr, owed, true, r2, lane);
-      }
-      if (small) {
-        if (opc == kSvcSend) {
-          svc_send_small(sp, os.sc, c, pslot, peer, res, lane);
-          done_small = true;
-          if (owed) {
-            OpResult r2;
-            svc_recv_small(sp, os.sc, pslot, nullptr, owed, true, r2, lane);
-          }
-        } else {
-          done_small = svc_recv_small(sp, os.sc, pslot, reinterpret_cast<uint8_t*>(c.ptr), c.n, opc == kSvcRetire, res, lane);
+      if (small || owed) {
+        const ConnView cv = conn_get(os.cc, cc_next, sp, pslot, peer, lane);
+        if (owed && !small) {
+          OpResult r2;
+          svc_recv_small(sp, cv, pslot, nullptr, owed, true, r2, lane);
         }
+        if (small) {
+          if (opc == kSvcSend) {
+            svc_send_small(sp, cv, c, pslot, res, lane);
+            done_small = true;
+            TRACE_MARK(0, tr0);  // small send: fetched -> frames landed, eager record + mirror stores issued
+            if (owed) {
+              OpResult r2;
+              svc_recv_small(sp, cv, pslot, nullptr, owed, true, r2, lane);
+              TRACE_MARK(1, tr0);  // ... -> piggybacked retire finished
+            }
+#ifdef B200_SVC_TRACE
+            if (lane == 0) atomicAdd(&g_svc_trace[2], 1ull);
+#endif
+          } else {
+            done_small = svc_recv_small(sp, cv, pslot, reinterpret_cast<uint8_t*>(c.ptr), c.n, opc == kSvcRetire, res, lane);
+          }
+        }
+        if (cv.P->wire != 0) conn_drop(os.cc, pslot, lane);  // nvlink wire: ring and credit change from outside
       }
       if (!done_small) {
         // ---- hand the op to the pool; the CTA that runs it answers the host itself
+        conn_drop(os.cc, pslot, lane);  // the job changes the connection's lines
         owner_reap(sp, boxes, os, -1, -1, lane);
         int bi = -1;
         while (true) {
@@ -1729,6 +1834,10 @@ __global__ void __launch_bounds__(128) k_svc_owner(SvcParams sp) {
         d.w = expect;
         st_sys_v4(&qdone[(expect - 1) % kOwnQ], d);
       }
+      TRACE_MARK(3, tr0);  // every answered op: fetched -> answer store issued
+#ifdef B200_SVC_TRACE
+      if (lane == 0) atomicAdd(&g_svc_trace[4], 1ull);
+#endif
     }
     expect++;
     cur++;
@@ -1987,6 +2096,15 @@ static void ensure_kernel_attrs() {
   cudaFuncGetAttributes(&fa, k_svc_big);
   cudaFuncGetAttributes(&fa, k_svc_poll);
   });
+}
+
+int svc_trace_read(unsigned long long* out16) {
+#ifdef B200_SVC_TRACE
+  return cudaMemcpyFromSymbol(out16, g_svc_trace, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1;
+#else
+  (void)out16;
+  return -1;
+#endif
 }
 
 bool launch_service(const SvcParams& sp, void* s_owner, void* s_big, void* s_poll) {

@@ -212,6 +212,9 @@ struct Runtime {
   uint32_t* d_svc_last_ev = nullptr;
   uint32_t svc_hi_slot = 0;
   std::atomic<uint64_t> svc_ops{0}, svc_ready_seen{0}, svc_ready_overflows{0}, svc_eager_hits{0};
+  // bumped whenever the host changes pair lines on the device or launches kernels beside the service; every
+  // command carries it (SvcCmd.op >> 8) and an owner warp that sees a new value drops its cached lines
+  std::atomic<uint32_t> svc_gen{1};
   uint32_t svc_ready_head = 0;      // next stream index the host expects (under scan_mu)
   std::vector<uint16_t> svc_level;  // events pending per slot, as last reported by the device poller
   std::mutex grave_mu;
@@ -661,6 +664,7 @@ extern "C" void b200_pair_init(b200_pair* p) {
       cudaMemcpyAsync(&r.d_svc_ps->hi_slot, &r.svc_hi_slot, 4, cudaMemcpyHostToDevice, r.stream);
     }
     cudaStreamSynchronize(r.stream);
+    r.svc_gen++;
   }
   // drop a stale registration, then publish the new address
   if (p->self.qpn) r.by_qpn.erase(p->self.qpn);
@@ -785,6 +789,7 @@ extern "C" int b200_pair_connect(b200_pair* p, const void* peer48, size_t n) {
     p->remote_credit = hd.peer_credit;
     p->peer_local = nullptr;
     p->status = B200_CONNECTED;
+    r.svc_gen++;
     return 1;
   }
   auto it = r.by_qpn.find(p->peer.qpn);
@@ -819,6 +824,7 @@ extern "C" int b200_pair_connect(b200_pair* p, const void* peer48, size_t n) {
   }
   p->peer_local = q;
   p->status = B200_CONNECTED;
+  r.svc_gen++;
   return 1;
 }
 
@@ -869,6 +875,7 @@ extern "C" void b200_pair_disconnect(b200_pair* p) {
   p->self.qpn = 0;
   p->peer_local = nullptr;
   p->status = B200_DISCONNECTED;
+  r.svc_gen++;
 }
 
 // On the nvlink wire the bytes, the credit and the peer_exit flag are written by another GPU, so
@@ -1057,6 +1064,7 @@ static uint64_t svc_post(Runtime& r, int q, Fill fill) {
   SvcCmd* c = &r.svc_cmds[e];
   c->nreal = 0;
   fill(c, r.svc_slices + e * kSvcSliceArea);
+  c->op = (c->op & 0xffu) | ((r.svc_gen.load(std::memory_order_acquire) & 0xffffffu) << 8);
   std::atomic_thread_fence(std::memory_order_release);
   *(volatile uint32_t*)&c->stamp2 = (uint32_t)(t + 1);
   *(volatile uint32_t*)&c->stamp = (uint32_t)(t + 1);
@@ -1099,19 +1107,28 @@ static int32_t slot_word(const b200_pair* p) {  // SvcCmd.slot: the pair's slot,
 }
 static void drain_retire(b200_pair* p) {
   Runtime& r = R();
-  const uint32_t owed = p->retire_owed.exchange(0, std::memory_order_acq_rel);
-  if (owed && r.svc_running.load()) {
+  if (p->retire_owed.load(std::memory_order_acquire) && r.svc_running.load()) {
+    // The owed Retire is claimed INSIDE the queue's posting section: whoever claims it has its Retire in
+    // the queue before anybody else can post another command for this connection (a Recv posted by the
+    // pair's own thread while another thread -- the peer's sender looking for credit -- sat between "claimed"
+    // and "posted" would deliver the frame a second time).
     const int q = owner_of(r, p);
-    p->retire_q = q;
-    p->retire_ticket = svc_post(r, q, [&](SvcCmd* c, SliceDev*) {
-      c->op = kSvcRetire;
+    bool posted = false;
+    const uint64_t t = svc_post(r, q, [&](SvcCmd* c, SliceDev*) {
+      const uint32_t owed = p->retire_owed.exchange(0, std::memory_order_acq_rel);
+      c->op = owed ? kSvcRetire : kSvcNop;
       c->slot = slot_word(p);
       c->flags = B200_BATCH_ONE_CALL;
       c->ptr = 0;
       c->n = owed;
       c->byte_idx = 0;
+      posted = owed != 0;
     });
-    p->retire_pending.store(true, std::memory_order_release);
+    if (posted) {
+      p->retire_q = q;
+      p->retire_ticket = t;
+      p->retire_pending.store(true, std::memory_order_release);
+    }
   }
   if (!p->retire_pending.load(std::memory_order_acquire)) return;
   if (r.svc_running.load()) svc_wait(r, p->retire_q, p->retire_ticket, nullptr, nullptr);
@@ -1186,6 +1203,8 @@ extern "C" void b200_service_stats(uint64_t out[4]) {
   out[3] = r.svc_host_scans ? *(volatile uint32_t*)r.svc_host_scans : 0;
 }
 extern "C" uint64_t b200_service_eager_hits(void) { return R().svc_eager_hits.load(); }
+// experiment builds (-DB200_SVC_TRACE): accumulated device-side phase timers of the owner warps, see b200_kernels.cu
+extern "C" int b200_debug_service_trace(unsigned long long* out16) { return svc_trace_read(out16); }
 
 // fill the slice list of a Send command: <= max_sge slices are looked at by one call, the rest only counts
 // towards total_slice_size (pair.cc:661-664) and is folded into one pseudo-slice that is never dereferenced
@@ -1236,9 +1255,10 @@ static bool svc_fill_send(b200_pair* p, SvcCmd* c, SliceDev* area, const b200_sl
 static uint64_t svc_send(Runtime& r, b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
   const int q = owner_of(r, p);
   bool ok = true;
-  // the Retire of an eagerly received frame rides on this Send (executed right after it by the owner warp)
-  const uint32_t owed = p->retire_owed.exchange(0, std::memory_order_acq_rel);
+  // the Retire of an eagerly received frame rides on this Send (executed right after it by the owner warp);
+  // claimed inside the posting section, see drain_retire
   const uint64_t t = svc_post(r, q, [&](SvcCmd* c, SliceDev* area) {
+    const uint32_t owed = p->retire_owed.exchange(0, std::memory_order_acq_rel);
     ok = svc_fill_send(p, c, area, slices, n, byte_idx, B200_BATCH_ONE_CALL | (owed << 16));
     if (!ok) {
       c->op = owed ? kSvcRetire : kSvcNop;
@@ -1689,6 +1709,7 @@ extern "C" int b200_batch_launch(b200_batch* b, void* stream) {
   if (!b) return -1;
   Runtime& r = R();
   if (b->nops == 0) return 0;
+  if (r.svc_running.load()) r.svc_gen++;  // kernels beside the service change pair lines behind the owners' caches
   if (b->kind == 1 && r.svc_running.load()) {
     // frames are about to be consumed behind the service's back: whatever it pushed eagerly for these pairs
     // is stale from now on, and stays so (host and device counts no longer agree -> Recv takes the normal path)
