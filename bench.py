@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-unary", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--no-endpoint", action="store_true", help="skip the e2e_endpoint leg")
+    ap.add_argument("--endpoint-threads", type=int, default=8, help="client/server thread pairs of the endpoint leg")
+    ap.add_argument("--endpoint-msgs", type=int, default=16)
+    ap.add_argument("--endpoint-pool", type=int, default=128, help="pool CTAs of the service during the endpoint leg")
     ap.add_argument("--msgs-per-step", type=int, default=1, help="experiment: messages per connection per step")
     ap.add_argument("--unary-bytes", type=int, default=1024)
     ap.add_argument("--unary-iters", type=int, default=2000)
@@ -453,6 +457,13 @@ def main():
         except Exception as exc:  # never take the streaming line down
             unary = {"error": repr(exc)}
 
+    e2e_endpoint = None
+    if rank == 0 and world == 1 and not args.no_endpoint:
+        try:
+            e2e_endpoint = run_e2e_endpoint(args, pkg, L, with_cpu=not args.no_cpu_baseline)
+        except Exception as exc:
+            e2e_endpoint = {"error": repr(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -485,6 +496,7 @@ def main():
                          "step_frac": (conns * (tx_alg + rx_alg) / (t_dev_ms / K * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "e2e_endpoint": e2e_endpoint,
             "unary": unary,
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -495,6 +507,63 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_e2e_endpoint(args, pkg, L, with_cpu):
+    """The same streaming workload THROUGH THE DROP-IN SURFACE: b200_endpoint_write / b200_endpoint_read +
+    b200_engine_work (include/b200_endpoint.h = rdma_bp_posix.cc + the BPEV poll loop), 256 connections, one
+    4 MiB chttp2-shaped message in flight per connection, 514 NON-ADJACENT host slices per message, every
+    delivered byte compared on the reader (tools/native/ep_stream.cc).  The engine batches: one pass = one
+    b200_pairs_submit of every ready rdma_flush / rdma_do_read loop, executed by the resident service kernels
+    (no launch), slices and read buffers used in place over PCIe.  Beside it the same driver over the
+    reference's own PairPollable on the host cores (tests/native/ref_pair_ops.cc, NDEBUG build)."""
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    C.CDLL(pkg.ENDPOINT_LIB_PATH, mode=C.RTLD_GLOBAL)
+    ES = C.CDLL(os.path.join(libdir, "libb200_epstream.so"))
+    ES.ep_stream_run.restype = C.c_double
+    ES.ep_stream_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    conns, threads, msgs = args.conns, args.endpoint_threads, args.endpoint_msgs
+    pkg.config_set("GRPC_RDMA_RING_BUFFER_SIZE_KB", args.ring_kb)
+    out = {"connections": conns, "message_bytes": args.msg_bytes, "msgs_per_connection": msgs, "unit": "GB/s",
+           "thread_pairs": threads,
+           "path": "b200_endpoint_write/read + b200_engine_work (batching engine -> b200_pairs_submit -> service kernels: "
+                   "owner warps + %d pool CTAs), 514 non-adjacent pinned slices per message, every byte verified" % args.endpoint_pool}
+    launches0 = L.b200_launch_count()
+    if L.b200_service_start(args.endpoint_pool) != 0:
+        return {"error": "b200_service_start: " + pkg.last_error()}
+    try:
+        o = (C.c_uint64 * 4)()
+        t = ES.ep_stream_run(None, conns, threads, msgs, 2, args.msg_bytes, 0, o)
+        if t <= 0:
+            out["b200"] = {"error": "driver rc %s, bad bytes %d" % (t, o[1])}
+        else:
+            out["b200"] = {"value": o[0] / t / 1e9, "seconds": t, "msgs_per_s": conns * msgs / t, "bad_bytes": int(o[1]),
+                           "submits_client": int(o[2]), "submits_server": int(o[3])}
+            out["value"] = out["b200"]["value"]
+    finally:
+        L.b200_service_stop()
+    out["kernel_launches"] = int(L.b200_launch_count() - launches0)   # the three resident kernels
+    if with_cpu:
+        relp = os.path.join(ROOT, "tests", "native", "libref_pair_ops_rel.so")
+        if os.path.exists(relp):
+            try:
+                R = C.CDLL(relp)
+                R.ref_pair_ops.restype = C.c_void_p
+                R.ref_ops_config.argtypes = [C.c_uint32]
+                R.ref_ops_config(args.ring_kb)
+                cores = usable_cpus()
+                ref = {"kind": "reference", "cores": cores}
+                for label, th in (("same_threads", threads), ("all_cores", max(1, min(conns, cores // 2)))):
+                    o = (C.c_uint64 * 4)()
+                    t = ES.ep_stream_run(R.ref_pair_ops(), conns, th, max(2, msgs // 2), 1, args.msg_bytes, 0, o)
+                    ref[label] = ({"value": o[0] / t / 1e9, "thread_pairs": th, "seconds": t, "bad_bytes": int(o[1])}
+                                  if t > 0 else {"error": "driver rc %s" % t, "thread_pairs": th})
+                out["cpu_reference"] = ref
+            except Exception as exc:
+                out["cpu_reference"] = {"error": repr(exc)}
+        else:
+            out["cpu_reference"] = {"error": "tests/native/libref_pair_ops_rel.so not built"}
+    return out
 
 
 def _pct(rtt_ns):

@@ -104,6 +104,8 @@ _SIGS = {
     "b200_service_eager_hits": (C.c_uint64, []),
     "b200_pairs_send": (C.c_int, [C.POINTER(SendOp), C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]),
     "b200_pairs_recv": (C.c_int, [C.POINTER(RecvOp), C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]),
+    "b200_pairs_submit": (C.c_int, [C.POINTER(SendOp), C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(RecvOp), C.c_size_t,
+                                    C.POINTER(C.c_uint64), C.c_int]),
     "b200_batch_prepare_send": (C.c_void_p, [C.POINTER(SendOp), C.c_size_t, C.c_int]),
     "b200_batch_prepare_recv": (C.c_void_p, [C.POINTER(RecvOp), C.c_size_t, C.c_int]),
     "b200_batch_launch": (C.c_int, [C.c_void_p, C.c_void_p]),

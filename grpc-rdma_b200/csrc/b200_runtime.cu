@@ -201,6 +201,7 @@ struct Runtime {
   OwnerQ* svc_q = nullptr;
   SvcCmd* svc_cmds = nullptr;          // pinned, mapped  [nowners][kOwnQ]
   SvcDone* svc_done = nullptr;         // pinned, mapped  [nowners][kOwnQ]
+  std::atomic<uint32_t>* svc_consumed = nullptr;  // host only [nowners][kOwnQ]: stamp of the last answer its waiter has read
   SliceDev* svc_slices = nullptr;      // pinned, mapped  [nowners][kOwnQ][kSvcSliceArea]
   EagerRec* svc_erec = nullptr;        // pinned, mapped  [kMaxPairs]
   uint8_t* svc_eslots = nullptr;       // pinned, mapped  [kMaxPairs][kEagerMax]
@@ -280,15 +281,18 @@ void rt_free(void* p, int host) {
   else cudaFree(p);
 }
 
+std::atomic<uint64_t> g_reg_epoch{1};
 void reg_add(const void* p, size_t n, int kind) {
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.reg_mu);
   r.reg_ranges[(uintptr_t)p] = {n, kind};
+  g_reg_epoch++;
 }
 void reg_del(const void* p) {
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.reg_mu);
   r.reg_ranges.erase((uintptr_t)p);
+  g_reg_epoch++;
 }
 // nvlink wire bootstrap.  The 48-byte address blob has no room for CUDA IPC handles, so -- like the
 // reference's memory-region exchange after the QP is up (pair.cc:472-486,513-526) -- the handles
@@ -307,14 +311,25 @@ std::string wire_path(uint32_t cookie, uint32_t qpn) {
   return b;
 }
 
-// 0 = not in the registry, 1 = pinned host, 2 = device
+// 0 = not in the registry, 1 = pinned host, 2 = device.  The slices of a message usually come from one
+// allocation: the last range a thread hit answers without the lock (reg_epoch: any change drops it).
 int reg_kind(const void* p) {
+  static thread_local uintptr_t c_base = 0, c_end = 0;
+  static thread_local int c_kind = 0;
+  static thread_local uint64_t c_epoch = 0;
+  const uint64_t ep = g_reg_epoch.load(std::memory_order_acquire);
+  if (c_epoch == ep && (uintptr_t)p >= c_base && (uintptr_t)p < c_end) return c_kind;
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.reg_mu);
   auto it = r.reg_ranges.upper_bound((uintptr_t)p);
   if (it == r.reg_ranges.begin()) return 0;
   --it;
-  return (uintptr_t)p < it->first + it->second.first ? it->second.second : 0;
+  if ((uintptr_t)p >= it->first + it->second.first) return 0;
+  c_base = it->first;
+  c_end = it->first + it->second.first;
+  c_kind = it->second.second;
+  c_epoch = ep;
+  return c_kind;
 }
 
 }  // namespace
@@ -1015,6 +1030,8 @@ extern "C" int b200_service_start(int workers) {
       !CU_OK(cudaStreamSynchronize(r.stream)))
     return -1;
   r.svc_q = new Runtime::OwnerQ[owners];
+  r.svc_consumed = new std::atomic<uint32_t>[nent];
+  for (size_t i = 0; i < nent; i++) r.svc_consumed[i].store(0);
   r.svc_workers = workers;
   r.svc_nowners = owners;
   r.svc_ready_head = 0;
@@ -1048,19 +1065,17 @@ extern "C" int b200_service_running(void) { return R().svc_running.load() ? R().
 
 // ---- owner queues: post = claim the next ticket of the queue and fill its entry; the answer lands in the
 // entry's SvcDone.  An entry is reused every kOwnQ tickets, once the answer of its previous ticket was seen.
+// An entry is reused every kOwnQ tickets -- once the answer of its previous ticket has been CONSUMED by the
+// thread that waits for it (svc_consumed), not merely written by the GPU: a thread that posts many commands
+// before it waits (b200_pairs_submit) would otherwise have its early answers overwritten by its later ones.
 template <class Fill>
-static uint64_t svc_post(Runtime& r, int q, Fill fill) {
+static bool svc_try_post(Runtime& r, int q, Fill fill, uint64_t* ticket) {
   Runtime::OwnerQ& Q = r.svc_q[q];
   std::lock_guard<std::mutex> lk(Q.mu);
-  const uint64_t t = Q.next++;
+  const uint64_t t = Q.next;
   const size_t e = (size_t)q * kOwnQ + t % kOwnQ;
-  volatile SvcDone* d = &r.svc_done[e];
-  if (t >= kOwnQ)
-    while (d->seq != (uint32_t)(t - kOwnQ + 1)) {
-#if defined(__x86_64__)
-      __builtin_ia32_pause();
-#endif
-    }
+  if (t >= kOwnQ && r.svc_consumed[e].load(std::memory_order_acquire) != (uint32_t)(t - kOwnQ + 1)) return false;
+  Q.next = t + 1;
   SvcCmd* c = &r.svc_cmds[e];
   c->nreal = 0;
   fill(c, r.svc_slices + e * kSvcSliceArea);
@@ -1068,19 +1083,30 @@ static uint64_t svc_post(Runtime& r, int q, Fill fill) {
   std::atomic_thread_fence(std::memory_order_release);
   *(volatile uint32_t*)&c->stamp2 = (uint32_t)(t + 1);
   *(volatile uint32_t*)&c->stamp = (uint32_t)(t + 1);
+  *ticket = t;
+  return true;
+}
+// blocking form: only for callers that hold no unconsumed answers themselves (they wait right after posting)
+template <class Fill>
+static uint64_t svc_post(Runtime& r, int q, Fill fill) {
+  uint64_t t = 0;
+  while (!svc_try_post(r, q, fill, &t)) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
   return t;
 }
 
 static bool svc_wait(Runtime& r, int q, uint64_t t, uint64_t* bytes, uint64_t* calls) {
-  volatile SvcDone* d = &r.svc_done[(size_t)q * kOwnQ + t % kOwnQ];
+  const size_t e = (size_t)q * kOwnQ + t % kOwnQ;
+  volatile SvcDone* d = &r.svc_done[e];
   const uint32_t want = (uint32_t)(t + 1);
   uint32_t spins = 0;
   std::chrono::steady_clock::time_point t0;
-  // (an entry can only be reused after this answer was seen by the poster of ticket t + kOwnQ, which is
-  // blocked behind us in svc_post: the stamp stays until we have read it -- unless somebody else waits for
-  // the same ticket, which only drain_retire does, under the pair's own ordering)
   while (d->seq != want) {
-    if ((int32_t)(d->seq - want) > 0) break;  // already reused: the answer was seen (Retire has no result)
+    // already reused: somebody else waited for this ticket too and consumed it (a Retire: no result to read)
+    if ((int32_t)(d->seq - want) > 0) return true;
 #if defined(__x86_64__)
     __builtin_ia32_pause();
 #endif
@@ -1095,6 +1121,7 @@ static bool svc_wait(Runtime& r, int q, uint64_t t, uint64_t* bytes, uint64_t* c
   std::atomic_thread_fence(std::memory_order_acquire);
   if (bytes) *bytes = d->bytes;
   if (calls) *calls = d->calls;
+  r.svc_consumed[e].store(want, std::memory_order_release);  // the entry may be reused now
   r.svc_ops++;
   return true;
 }
@@ -1124,15 +1151,11 @@ static void drain_retire(b200_pair* p) {
       c->byte_idx = 0;
       posted = owed != 0;
     });
-    if (posted) {
-      p->retire_q = q;
-      p->retire_ticket = t;
-      p->retire_pending.store(true, std::memory_order_release);
-    }
+    // wait for what was posted (the Retire, or the no-op behind somebody else's Retire: the queue is in order,
+    // so either way the pair's Retire has run when this returns)
+    (void)posted;
+    svc_wait(r, q, t, nullptr, nullptr);
   }
-  if (!p->retire_pending.load(std::memory_order_acquire)) return;
-  if (r.svc_running.load()) svc_wait(r, p->retire_q, p->retire_ticket, nullptr, nullptr);
-  p->retire_pending.store(false, std::memory_order_release);
 }
 
 extern "C" void b200_service_stop(void) {
@@ -1153,6 +1176,8 @@ extern "C" void b200_service_stop(void) {
   r.svc_running = false;
   delete[] r.svc_q;
   r.svc_q = nullptr;
+  delete[] r.svc_consumed;
+  r.svc_consumed = nullptr;
   {
     // the host poller thread reads the ready ring under scan_mu: hand it a null pointer before the free
     std::lock_guard<std::mutex> lk(r.scan_mu);
@@ -1210,25 +1235,43 @@ extern "C" int b200_debug_service_trace(unsigned long long* out16) { return svc_
 // towards total_slice_size (pair.cc:661-664) and is folded into one pseudo-slice that is never dereferenced
 // (SvcCmd.nreal); unregistered memory is staged in the calling thread's pinned bounce buffer
 static bool svc_fill_send(b200_pair* p, SvcCmd* c, SliceDev* area, const b200_slice* slices, size_t n, size_t byte_idx,
-                          uint32_t flags) {
+                          uint32_t flags, uint64_t* bounce_cursor = nullptr) {
+  const bool one_call = !(flags & B200_BATCH_UNTIL_BLOCKED);  // (flags >> 16: owed Retire)
   size_t look = n;
-  if (!(flags & B200_BATCH_UNTIL_BLOCKED) && look > (size_t)p->max_sge) look = (size_t)p->max_sge;  // (flags >> 16: owed Retire)
+  if (one_call && look > (size_t)p->max_sge) look = (size_t)p->max_sge;
   if (look > kSvcSliceArea - 1) look = kSvcSliceArea - 1;
+  TlsBounce& tb = tls_bounce();
+  uint64_t bounce_off = bounce_cursor ? *bounce_cursor : 0;
+  // unregistered host memory is staged in the calling thread's pinned buffer like the reference copies
+  // into its registered send buffer; what does not fit is left for the next call (the op then ends there)
+  for (size_t i = 0; i < look; i++) {
+    const uint64_t len = slices[i].len;
+    if (!len || mem_kind(slices[i].ptr) != 0) continue;
+    const uint64_t skip = i == 0 ? byte_idx : 0;
+    uint64_t take = len - skip;
+    if (one_call && take > p->cap / 2) take = p->cap / 2;  // a call never accepts more than the staging size
+    if (bounce_off + take > tb.tx_cap) {
+      if (bounce_cursor == nullptr && bounce_off == 0) {
+        if (!ensure_bounce(&tb.tx, &tb.tx_cap, (one_call ? p->cap : take) + 16 * (kMaxSgeLimit + 4))) return false;
+      } else if (!one_call) {
+        look = i;  // staged prefix only; the rest only counts towards total_slice_size
+        break;
+      }
+    }
+    bounce_off += (take + 15) & ~15ull;
+  }
+  bounce_off = bounce_cursor ? *bounce_cursor : 0;
   uint64_t rest = 0;
   for (size_t i = look; i < n; i++) rest += slices[i].len;
   const size_t nsl = look + (rest ? 1 : 0);
   SliceDev* out = nsl <= kSvcInline ? c->inl : area;
-  TlsBounce& tb = tls_bounce();
-  uint64_t bounce_off = 0;
   for (size_t i = 0; i < look; i++) {
     const uint8_t* ptr = (const uint8_t*)slices[i].ptr;
     const uint64_t len = slices[i].len;
-    if (len && mem_kind(ptr) == 0) {  // unregistered host memory: stage like the reference's send buffer
+    if (len && mem_kind(ptr) == 0) {
       const uint64_t skip = i == 0 ? byte_idx : 0;
-      const uint64_t useful = len - skip;
-      const uint64_t limit = p->cap / 2;  // a call never accepts more than the staging size
-      uint64_t take = useful < limit ? useful : limit;
-      if (!ensure_bounce(&tb.tx, &tb.tx_cap, p->cap + 16 * (kMaxSgeLimit + 4))) return false;
+      uint64_t take = len - skip;
+      if (one_call && take > p->cap / 2) take = p->cap / 2;
       if (bounce_off + take > tb.tx_cap) take = tb.tx_cap - bounce_off;
       memcpy(tb.tx + bounce_off, ptr + skip, take);
       out[i].ptr = tb.tx + bounce_off - skip;  // keep (ptr + skip) pointing at the staged bytes
@@ -1238,6 +1281,7 @@ static bool svc_fill_send(b200_pair* p, SvcCmd* c, SliceDev* area, const b200_sl
     }
     out[i].len = len;
   }
+  if (bounce_cursor) *bounce_cursor = bounce_off;
   if (rest) {
     out[look].ptr = nullptr;
     out[look].len = rest;
@@ -1808,6 +1852,115 @@ extern "C" int b200_pairs_send(const b200_send_op* ops, size_t nops, int flags, 
 }
 extern "C" int b200_pairs_recv(const b200_recv_op* ops, size_t nops, int flags, uint64_t* delivered, void* stream) {
   return run_unprepared(1, ops, nops, flags, delivered, stream);
+}
+
+// One engine pass worth of work: every Send and every Recv the event loop has ready, posted together and
+// waited for together.  With the service running nothing is launched: each op becomes a command of the pair's
+// owner queue (large ones run on the pool CTAs, all of them side by side), slices and destinations are read
+// and written in place over PCIe.  Without it the two batch launches are used.
+extern "C" int b200_pairs_submit(const b200_send_op* sops, size_t ns, uint64_t* accepted, const b200_recv_op* rops,
+                                 size_t nr, uint64_t* delivered, int flags) {
+  if (!ensure_init()) return -1;
+  Runtime& r = R();
+  if (!r.svc_running.load()) {
+    int rc = 0;
+    if (ns) rc = b200_pairs_send(sops, ns, flags, accepted, nullptr);
+    if (rc == 0 && nr) rc = b200_pairs_recv(rops, nr, flags, delivered, nullptr);
+    return rc;
+  }
+  struct Ticket {
+    int q;
+    uint64_t t;
+    bool posted;
+  };
+  static thread_local std::vector<Ticket> st, rt;
+  st.assign(ns, Ticket{0, 0, false});
+  rt.assign(nr, Ticket{0, 0, false});
+  // staging for unregistered slices: one pinned buffer for the whole pass
+  uint64_t need = 0;
+  for (size_t i = 0; i < ns; i++)
+    for (size_t j = 0; j < sops[i].nslices && j < kSvcSliceArea; j++)
+      if (sops[i].slices[j].len && mem_kind(sops[i].slices[j].ptr) == 0) need += (sops[i].slices[j].len + 15) & ~15ull;
+  TlsBounce& tb = tls_bounce();
+  const uint64_t kMaxBounce = 1ull << 30;
+  if (need && !ensure_bounce(&tb.tx, &tb.tx_cap, need < kMaxBounce ? need : kMaxBounce)) return -1;
+  uint64_t cursor = 0;
+  const uint32_t fl = (uint32_t)(flags & (B200_BATCH_UNTIL_BLOCKED));
+  int rc = 0;
+  // answers are collected at the end -- or earlier, when a queue has no free entry: a thread never blocks on
+  // a queue while it sits on answers of its own that somebody else's post may be waiting for
+  auto harvest = [&]() {
+    for (size_t i = 0; i < ns; i++) {
+      if (!st[i].posted) continue;
+      st[i].posted = false;
+      uint64_t bytes = 0;
+      if (!svc_wait(r, st[i].q, st[i].t, &bytes, nullptr)) rc = -1;
+      if (accepted) accepted[i] = bytes;
+    }
+    for (size_t i = 0; i < nr; i++) {
+      if (!rt[i].posted) continue;
+      rt[i].posted = false;
+      uint64_t bytes = 0;
+      if (!svc_wait(r, rt[i].q, rt[i].t, &bytes, nullptr)) rc = -1;
+      rops[i].pair->svc_delivered += bytes;
+      if (delivered) delivered[i] = bytes;
+    }
+  };
+  for (size_t i = 0; i < ns; i++) {
+    b200_pair* p = sops[i].pair;
+    if (accepted) accepted[i] = 0;
+    if (!p || p->status != B200_CONNECTED || sops[i].nslices == 0) continue;
+    if (((volatile PairMirror*)p->mirror)->peer_exit == 1) continue;
+    if (p->peer_local && p->peer_local->retire_owed.load(std::memory_order_acquire)) {
+      harvest();
+      drain_retire(p->peer_local);
+    }
+    if (send_is_a_no_op(p)) continue;
+    const int q = owner_of(r, p);
+    bool ok = true;
+    auto fill = [&](SvcCmd* c, SliceDev* area) {
+      const uint32_t owed = p->retire_owed.exchange(0, std::memory_order_acq_rel);
+      ok = svc_fill_send(p, c, area, sops[i].slices, sops[i].nslices, sops[i].byte_idx, fl | (owed << 16), &cursor);
+      if (!ok) {
+        c->op = owed ? kSvcRetire : kSvcNop;
+        c->slot = slot_word(p);
+        c->flags = B200_BATCH_ONE_CALL;
+        c->n = owed;
+      }
+    };
+    while (!svc_try_post(r, q, fill, &st[i].t)) harvest();
+    st[i].q = q;
+    st[i].posted = true;
+  }
+  for (size_t i = 0; i < nr; i++) {
+    b200_pair* p = rops[i].pair;
+    if (delivered) delivered[i] = 0;
+    if (!p || p->status != B200_CONNECTED || rops[i].cap == 0) continue;
+    if (p->retire_owed.load(std::memory_order_acquire)) {
+      harvest();
+      drain_retire(p);
+    }
+    if (!p->remote && ((volatile PairMirror*)p->mirror)->has_message == 0) continue;
+    if (mem_kind(rops[i].dst) == 0) {
+      set_err("b200_pairs_submit: destinations must be GPU-addressable (b200_mem_alloc_host / register_host / device)");
+      rc = -1;
+      continue;
+    }
+    const int q = owner_of(r, p);
+    auto fill = [&](SvcCmd* c, SliceDev*) {
+      c->op = kSvcRecv;
+      c->slot = slot_word(p);
+      c->flags = fl;
+      c->ptr = (uint64_t)(uintptr_t)rops[i].dst;
+      c->n = rops[i].cap;
+      c->byte_idx = 0;
+    };
+    while (!svc_try_post(r, q, fill, &rt[i].t)) harvest();
+    rt[i].q = q;
+    rt[i].posted = true;
+  }
+  harvest();
+  return rc;
 }
 
 // ================================================================ calibration

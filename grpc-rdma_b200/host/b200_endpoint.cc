@@ -1,6 +1,16 @@
 // b200_endpoint.cc -- endpoint state machine + BPEV hybrid poll loop over the pair ABI.
 // See include/b200_endpoint.h for the reference functions each piece mirrors
 // (src/core/lib/iomgr/rdma_bp_posix.cc, ev_epollex_rdma_bpev_linux.cc).
+//
+// Two ways of running the pair operations:
+//   * call by call (ops->send / ops->recv from the closures, exactly the reference's structure) -- used when
+//     the ops table has no `submit` (the CPU tables of the tests: oracle, the reference's own PairPollable);
+//   * batched (ops->submit present: the CUDA library): rdma_read / rdma_write / the readiness scan only
+//     QUEUE the endpoint, and one b200_engine_work pass executes every queued rdma_flush loop and
+//     rdma_do_read loop with ONE submit -- all connections' ops run on the GPU side by side instead of one
+//     round trip after the other.  Read slices come from a pool of pinned, 256-byte aligned blocks and
+//     their size adapts to what the last reads delivered (what gRPC's own tcp_posix.cc does with
+//     target_length; the reference's max(256, GetReadableSize()) is the starting point and the floor).
 #include "../../include/b200_endpoint.h"
 
 #include <errno.h>
@@ -9,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/epoll.h>
+#include <sys/eventfd.h>
 #include <sys/socket.h>
 #include <unistd.h>
 
@@ -25,6 +36,8 @@ namespace {
 
 constexpr int kMaxEpollEvents = 100;  // MAX_EPOLL_EVENTS, ev_epollex_rdma_bpev_linux.cc
 constexpr size_t kMaxReadIovec = 4;   // MAX_READ_IOVEC, rdma_bp_posix.cc:178
+constexpr intptr_t kTagPair = 2;      // eventfd of a pair, tag ptr|2 (:725-741)
+constexpr intptr_t kTagWake = 4;      // the engine's own wakeup fd
 
 // ---- default pair ops: the CUDA library
 void* d_take(const char* id) { return b200_pool_take(id); }
@@ -44,22 +57,94 @@ void d_consume(void* p) { b200_pair_consume_wakeup((b200_pair*)p); }
 void d_disconnect(void* p) { b200_pair_disconnect((b200_pair*)p); }
 void d_padd(void* p) { b200_poller_add((b200_pair*)p); }
 void d_premove(void* p) { b200_poller_remove((b200_pair*)p); }
-const b200_pair_ops kCudaOps = {d_take,   d_putback, d_init,     d_addr,   d_connect, d_send,
-                                d_recv,   d_has_msg, d_pending,  d_readable, d_status, d_error,
-                                d_wfd,    d_consume, d_disconnect, d_padd, d_premove};
+// batching needs the resident service kernels (no launch per pass, slices used in place); without them the
+// engine runs the queued continuations call by call (rc 1 = "not available")
+int d_submit(const b200_send_op* s, size_t ns, uint64_t* acc, const b200_recv_op* r, size_t nr, uint64_t* del, int flags) {
+  if (!b200_service_running()) return 1;
+  return b200_pairs_submit(s, ns, acc, r, nr, del, flags);
+}
+void* d_malloc(size_t n) { return b200_mem_alloc_host(n); }
+void d_mfree(void* p) { b200_mem_free_host(p); }
+const b200_pair_ops kCudaOps = {d_take,   d_putback, d_init,       d_addr,     d_connect, d_send,
+                                d_recv,   d_has_msg, d_pending,    d_readable, d_status,  d_error,
+                                d_wfd,    d_consume, d_disconnect, d_padd,     d_premove, d_submit,
+                                d_malloc, d_mfree};
+
+// Pool of read-slice blocks: power-of-two size classes from 256 bytes, GPU-addressable when the ops table
+// provides an allocator (every b200_mem_alloc_host block is 256-byte aligned: the alignment the PCIe DMA
+// wants, profiles/r1k_pcie_alignment.txt), plain aligned host memory otherwise.
+struct Pool {
+  const b200_pair_ops* ops;
+  std::mutex mu;
+  std::vector<void*> free_[32];
+  std::vector<void*> all;
+  explicit Pool(const b200_pair_ops* o) : ops(o) {}
+  ~Pool() {
+    for (void* p : all) {
+      if (ops->mem_free) ops->mem_free(p);
+      else free(p);
+    }
+  }
+  static int cls(size_t bytes) {
+    int c = 8;  // 256
+    while (((size_t)1 << c) < bytes) c++;
+    return c;
+  }
+  void* get(size_t bytes, int* c_out) {
+    const int c = cls(bytes);
+    *c_out = c;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!free_[c].empty()) {
+        void* p = free_[c].back();
+        free_[c].pop_back();
+        return p;
+      }
+    }
+    void* p = nullptr;
+    if (ops->mem_alloc) p = ops->mem_alloc((size_t)1 << c);
+    else if (posix_memalign(&p, 256, (size_t)1 << c) != 0) p = nullptr;
+    if (p) {
+      std::lock_guard<std::mutex> lk(mu);
+      all.push_back(p);
+    }
+    return p;
+  }
+  void put(void* p, int c) {
+    std::lock_guard<std::mutex> lk(mu);
+    free_[c].push_back(p);
+  }
+};
 
 // A read slice: the endpoint allocates it itself (rdma_bp_posix.cc:308-317) and hands views out.
 struct Buf {
-  std::shared_ptr<std::vector<uint8_t>> store;
+  std::shared_ptr<uint8_t> store;
   size_t off = 0, len = 0;
-  uint8_t* ptr() const { return store->data() + off; }
+  uint8_t* ptr() const { return store.get() + off; }
 };
+
+Buf make_buf(const std::shared_ptr<Pool>& pool, size_t bytes) {
+  int c = 0;
+  void* p = pool->get(bytes, &c);
+  Buf b;
+  if (!p) abort();
+  std::shared_ptr<Pool> keep = pool;
+  b.store = std::shared_ptr<uint8_t>((uint8_t*)p, [keep, c](uint8_t* q) { keep->put(q, c); });
+  b.off = 0;
+  b.len = bytes;
+  return b;
+}
 
 // lockfree_event stand-in (grpc_fd read_closure / write_closure): an edge is remembered until
 // somebody asks for it.
 struct Event {
   bool ready = false;
   bool armed = false;
+};
+
+struct Task {
+  std::function<void()> f;
+  bool user;  // a user callback: runs WITHOUT the engine lock
 };
 
 }  // namespace
@@ -82,6 +167,8 @@ struct b200_endpoint {
   std::vector<Buf> last_read_buffer;  // garbage after the last read
   std::vector<b200_slice> incoming_view;
   Event rd;
+  size_t target_length = 0;  // batching: adaptive read size (tcp_posix.cc target_length)
+  bool queued_read = false, queued_write = false;
   // write side
   b200_closure_fn write_cb = nullptr;
   void* write_arg = nullptr;
@@ -90,36 +177,61 @@ struct b200_endpoint {
   size_t outgoing_idx = 0;       // slices already removed from the front
   size_t outgoing_byte_idx = 0;  // byte within outgoing[outgoing_idx] to write next
   Event wr;
-  std::string err_scratch;
 };
 
 struct b200_engine {
   const b200_pair_ops* ops = nullptr;
   int epfd = -1;
+  int wake_fd = -1;  // kicked when work is queued for an engine that may be asleep in epoll_wait
   int busy_poll_us = 500;
-  std::recursive_mutex mu;  // rdma_mu + the pollable's own lock
+  std::mutex mu;  // rdma_mu + the pollable's own lock: engine and endpoint state; never held across
+                  // epoll_wait, a submit or a user callback
   std::vector<b200_endpoint*> rdma_fds;
-  std::deque<std::function<void()>> exec;  // ExecCtx closure list
+  std::deque<Task> exec;  // ExecCtx closure list
   bool flushing = false;
+  bool batch = false;
+  bool in_work = false;  // a thread is between the end of its wait and the end of its pass
+  size_t max_read_chunk = 4u << 20;
+  std::vector<b200_endpoint*> q_reads, q_writes;  // batching: rdma_do_read / rdma_flush loops to run
+  std::shared_ptr<Pool> pool;
   uint64_t stats[4] = {0, 0, 0, 0};
+  uint64_t bstats[3] = {0, 0, 0};
 };
 
 namespace {
 
-using Lock = std::lock_guard<std::recursive_mutex>;
+using Lock = std::unique_lock<std::mutex>;
 
-void schedule(b200_engine* e, std::function<void()> f) { e->exec.push_back(std::move(f)); }
+void schedule(b200_engine* e, std::function<void()> f) { e->exec.push_back(Task{std::move(f), false}); }
+void schedule_user(b200_engine* e, b200_closure_fn cb, void* arg, const char* error) {
+  if (error) {
+    std::string es(error);
+    e->exec.push_back(Task{[cb, arg, es] { cb(arg, es.c_str()); }, true});
+  } else {
+    e->exec.push_back(Task{[cb, arg] { cb(arg, nullptr); }, true});
+  }
+}
 
-// grpc_core::ExecCtx::Flush
-void flush(b200_engine* e) {
-  if (e->flushing) return;
+// grpc_core::ExecCtx::Flush.  Called with the lock held; user callbacks run unlocked.
+void flush(b200_engine* e, Lock& lk) {
+  if (e->flushing) return;  // the thread that is flushing picks the new tasks up
   e->flushing = true;
   while (!e->exec.empty()) {
-    auto f = std::move(e->exec.front());
+    Task t = std::move(e->exec.front());
     e->exec.pop_front();
-    f();
+    if (t.user) {
+      lk.unlock();
+      t.f();
+      lk.lock();
+    } else {
+      t.f();
+    }
   }
   e->flushing = false;
+}
+
+void kick_engine(b200_engine* e) {
+  if (e->wake_fd >= 0) (void)eventfd_write(e->wake_fd, 1);
 }
 
 size_t buf_length(const std::vector<Buf>& v) {
@@ -137,6 +249,22 @@ void ep_unref(b200_endpoint* ep);
 void rdma_handle_read(b200_endpoint* ep, const char* error);
 void rdma_handle_write(b200_endpoint* ep, const char* error);
 
+// the readiness edge reaches the endpoint: run (or, batching, queue) its read / write continuation
+void dispatch(b200_endpoint* ep, bool is_read) {
+  b200_engine* e = ep->engine;
+  if (e->batch) {
+    bool& q = is_read ? ep->queued_read : ep->queued_write;
+    if (!q) {
+      q = true;
+      const bool was_idle = e->q_reads.empty() && e->q_writes.empty();
+      (is_read ? e->q_reads : e->q_writes).push_back(ep);
+      if (was_idle && !e->in_work) kick_engine(e);  // the engine may be asleep in epoll_wait
+    }
+  } else {
+    schedule(e, [ep, is_read] { is_read ? rdma_handle_read(ep, nullptr) : rdma_handle_write(ep, nullptr); });
+  }
+}
+
 // grpc_fd_notify_on_read / _write over the lockfree event
 void notify_on(b200_endpoint* ep, Event& ev, bool is_read) {
   b200_engine* e = ep->engine;
@@ -147,7 +275,7 @@ void notify_on(b200_endpoint* ep, Event& ev, bool is_read) {
   }
   if (ev.ready) {
     ev.ready = false;
-    schedule(e, [ep, is_read] { is_read ? rdma_handle_read(ep, nullptr) : rdma_handle_write(ep, nullptr); });
+    dispatch(ep, is_read);
   } else {
     ev.armed = true;
   }
@@ -157,7 +285,7 @@ void notify_on(b200_endpoint* ep, Event& ev, bool is_read) {
 void set_ready(b200_endpoint* ep, Event& ev, bool is_read) {
   if (ev.armed) {
     ev.armed = false;
-    schedule(ep->engine, [ep, is_read] { is_read ? rdma_handle_read(ep, nullptr) : rdma_handle_write(ep, nullptr); });
+    dispatch(ep, is_read);
   } else {
     ev.ready = true;
   }
@@ -171,12 +299,7 @@ void call_read_cb(b200_endpoint* ep, const char* error) {
   ep->incoming_view.clear();
   if (!error)
     for (auto& b : ep->incoming) ep->incoming_view.push_back({b.ptr(), b.len});
-  if (error) {
-    std::string es(error);
-    schedule(ep->engine, [cb, arg, es] { cb(arg, es.c_str()); });
-  } else {
-    schedule(ep->engine, [cb, arg] { cb(arg, nullptr); });
-  }
+  schedule_user(ep->engine, cb, arg, error);
 }
 
 // grpc_slice_buffer_trim_end(incoming, n, &last_read_buffer)
@@ -198,7 +321,32 @@ void trim_end(std::vector<Buf>& buf, size_t n, std::vector<Buf>& garbage) {
   }
 }
 
-// rdma_do_read, rdma_bp_posix.cc:180-286
+// the part of rdma_do_read after its Recv loop (rdma_bp_posix.cc:216-286): `total_read_bytes` came back
+void finish_read(b200_endpoint* ep, size_t total_read_bytes, size_t incoming_length) {
+  const b200_pair_ops* ops = ep->engine->ops;
+  if (total_read_bytes == 0) {
+    ep->inq = ops->readable(ep->pair) > 0;
+    const int status = ops->status(ep->pair);
+    if (status == B200_HALF_CLOSED) {  // :218-228
+      ep->incoming.clear();
+      call_read_cb(ep, annotate(ep, "Pair closed").c_str());
+      ep_unref(ep);
+      return;
+    } else if (status == B200_ERROR) {  // :229-239
+      ep->incoming.clear();
+      call_read_cb(ep, annotate(ep, std::string("Pair error, ") + ops->error(ep->pair)).c_str());
+      ep_unref(ep);
+      return;
+    }
+    notify_on(ep, ep->rd, true);  // we've consumed the edge, request a new one
+    return;
+  }
+  if (total_read_bytes < incoming_length) trim_end(ep->incoming, incoming_length - total_read_bytes, ep->last_read_buffer);
+  call_read_cb(ep, nullptr);
+  ep_unref(ep);
+}
+
+// rdma_do_read, rdma_bp_posix.cc:180-286 (call-by-call form)
 void rdma_do_read(b200_endpoint* ep) {
   const b200_pair_ops* ops = ep->engine->ops;
   struct Iov {
@@ -215,21 +363,7 @@ void rdma_do_read(b200_endpoint* ep) {
     if (iov_len > 0) read_bytes = ops->recv(ep->pair, iov[0].base, iov[0].len);
     if (read_bytes == 0) {
       ep->inq = ops->readable(ep->pair) > 0;
-      if (total_read_bytes > 0) break;  // deliver what previous Recv calls got
-      const int status = ops->status(ep->pair);
-      if (status == B200_HALF_CLOSED) {  // :218-228
-        ep->incoming.clear();
-        call_read_cb(ep, annotate(ep, "Pair closed").c_str());
-        ep_unref(ep);
-        return;
-      } else if (status == B200_ERROR) {  // :229-239
-        ep->incoming.clear();
-        call_read_cb(ep, annotate(ep, std::string("Pair error, ") + ops->error(ep->pair)).c_str());
-        ep_unref(ep);
-        return;
-      }
-      notify_on(ep, ep->rd, true);  // we've consumed the edge, request a new one
-      return;
+      break;  // deliver what previous Recv calls got, or handle "nothing at all"
     }
     total_read_bytes += read_bytes;
     if (ep->inq == 0 || total_read_bytes == incoming_length) break;
@@ -250,21 +384,18 @@ void rdma_do_read(b200_endpoint* ep) {
     }
     iov_len = j;
   }
-  if (total_read_bytes < incoming_length) trim_end(ep->incoming, incoming_length - total_read_bytes, ep->last_read_buffer);
-  call_read_cb(ep, nullptr);
-  ep_unref(ep);
+  finish_read(ep, total_read_bytes, incoming_length);
 }
 
 // rdma_continue_read, rdma_bp_posix.cc:306-326: ONE slice of max(256, readable)
+void prepare_read_slice(b200_endpoint* ep) {
+  b200_engine* e = ep->engine;
+  size_t target = std::max<uint64_t>(256, e->ops->readable(ep->pair));
+  if (e->batch) target = std::min(e->max_read_chunk, std::max(target, ep->target_length));
+  if (buf_length(ep->incoming) == 0 && ep->incoming.size() < kMaxReadIovec) ep->incoming.push_back(make_buf(e->pool, target));
+}
 void rdma_continue_read(b200_endpoint* ep) {
-  const size_t target = std::max<uint64_t>(256, ep->engine->ops->readable(ep->pair));
-  if (buf_length(ep->incoming) == 0 && ep->incoming.size() < kMaxReadIovec) {
-    Buf b;
-    b.store = std::make_shared<std::vector<uint8_t>>(target);
-    b.off = 0;
-    b.len = target;
-    ep->incoming.push_back(b);
-  }
+  prepare_read_slice(ep);
   rdma_do_read(ep);
 }
 
@@ -280,11 +411,11 @@ void rdma_handle_read(b200_endpoint* ep, const char* error) {
   }
 }
 
-// rdma_flush, rdma_bp_posix.cc:470-524.  true = finished (ok or error), false = partial.
-bool rdma_flush(b200_endpoint* ep, std::string* error) {
+// the part of rdma_flush after Send (rdma_bp_posix.cc:480-524): `sent` bytes were accepted.
+// true = finished (ok or error), false = partial.
+bool finish_flush(b200_endpoint* ep, uint64_t sent, std::string* error) {
   const b200_pair_ops* ops = ep->engine->ops;
   size_t idx = ep->outgoing_idx;
-  uint64_t sent = ops->send(ep->pair, ep->outgoing + idx, ep->outgoing_count - idx, ep->outgoing_byte_idx);
   while (sent > 0) {  // :480-493
     const uint64_t slice_len = ep->outgoing[idx].len - ep->outgoing_byte_idx;
     if (sent >= slice_len) {
@@ -306,37 +437,43 @@ bool rdma_flush(b200_endpoint* ep, std::string* error) {
     else *error = annotate(ep, std::string("RDMA Pair has an internal error, ") + ops->error(ep->pair));
     return true;
   }
+  ep->outgoing_idx = idx;
   error->clear();
   return true;
 }
 
+// rdma_flush, rdma_bp_posix.cc:470-524
+bool rdma_flush(b200_endpoint* ep, std::string* error) {
+  const size_t idx = ep->outgoing_idx;
+  const uint64_t sent = ep->engine->ops->send(ep->pair, ep->outgoing + idx, ep->outgoing_count - idx, ep->outgoing_byte_idx);
+  return finish_flush(ep, sent, error);
+}
+
+void finish_write(b200_endpoint* ep, const char* err) {
+  b200_closure_fn cb = ep->write_cb;
+  void* arg = ep->write_arg;
+  ep->write_cb = nullptr;
+  schedule_user(ep->engine, cb, arg, err);
+  ep_unref(ep);
+}
+
 // rdma_handle_write, rdma_bp_posix.cc:527-557
 void rdma_handle_write(b200_endpoint* ep, const char* error) {
-  auto finish = [ep](const char* err) {
-    b200_closure_fn cb = ep->write_cb;
-    void* arg = ep->write_arg;
-    ep->write_cb = nullptr;
-    if (err) {
-      std::string es(err);
-      schedule(ep->engine, [cb, arg, es] { cb(arg, es.c_str()); });
-    } else {
-      schedule(ep->engine, [cb, arg] { cb(arg, nullptr); });
-    }
-    ep_unref(ep);
-  };
   if (error) {
-    finish(error);
+    finish_write(ep, error);
     return;
   }
   std::string err;
   if (!rdma_flush(ep, &err)) notify_on(ep, ep->wr, false);  // "write: delayed"
-  else finish(err.empty() ? nullptr : err.c_str());
+  else finish_write(ep, err.empty() ? nullptr : err.c_str());
 }
 
 // rdma_free, rdma_bp_posix.cc:112-132
 void ep_free(b200_endpoint* ep) {
   b200_engine* e = ep->engine;
   const b200_pair_ops* ops = e->ops;
+  e->q_reads.erase(std::remove(e->q_reads.begin(), e->q_reads.end(), ep), e->q_reads.end());
+  e->q_writes.erase(std::remove(e->q_writes.begin(), e->q_writes.end(), ep), e->q_writes.end());
   if (ep->pair) {
     // fd_orphan: drop the eventfd from the epoll set and the fd from the rdma list
     epoll_ctl(e->epfd, EPOLL_CTL_DEL, ops->wakeup_read_fd(ep->pair), nullptr);
@@ -354,6 +491,76 @@ void ep_unref(b200_endpoint* ep) {
   if (--ep->refs == 0) ep_free(ep);
 }
 
+// Batching: every queued rdma_flush loop and rdma_do_read loop of this pass in ONE submit.  The lock is
+// released while the GPU works; the queued endpoints are kept alive by the reference their pending
+// read / write holds.
+void run_batch(b200_engine* e, Lock& lk) {
+  if (e->q_reads.empty() && e->q_writes.empty()) return;
+  std::vector<b200_endpoint*> reads, writes;
+  reads.swap(e->q_reads);
+  writes.swap(e->q_writes);
+  std::vector<b200_send_op> sops;
+  std::vector<b200_recv_op> rops;
+  std::vector<b200_endpoint*> seps, reps;
+  std::vector<size_t> rlen;
+  for (b200_endpoint* ep : writes) {
+    ep->queued_write = false;
+    if (!ep->write_cb) continue;
+    b200_send_op o;
+    o.pair = (b200_pair*)ep->pair;
+    o.slices = ep->outgoing + ep->outgoing_idx;
+    o.nslices = ep->outgoing_count - ep->outgoing_idx;
+    o.byte_idx = ep->outgoing_byte_idx;
+    sops.push_back(o);
+    seps.push_back(ep);
+  }
+  for (b200_endpoint* ep : reads) {
+    ep->queued_read = false;
+    if (!ep->read_cb) continue;
+    prepare_read_slice(ep);
+    ep->inq = 1;
+    b200_recv_op o;
+    o.pair = (b200_pair*)ep->pair;
+    o.dst = ep->incoming.empty() ? nullptr : ep->incoming[0].ptr();
+    o.cap = ep->incoming.empty() ? 0 : ep->incoming[0].len;
+    rops.push_back(o);
+    reps.push_back(ep);
+    rlen.push_back(buf_length(ep->incoming));
+  }
+  if (sops.empty() && rops.empty()) return;
+  std::vector<uint64_t> acc(sops.size() + 1, 0), del(rops.size() + 1, 0);
+  e->bstats[0]++;
+  e->bstats[1] += sops.size();
+  e->bstats[2] += rops.size();
+  lk.unlock();
+  const int src = e->ops->submit(sops.data(), sops.size(), acc.data(), rops.data(), rops.size(), del.data(),
+                                 B200_BATCH_UNTIL_BLOCKED);
+  lk.lock();
+  if (src == 1) {  // no batching right now: the same continuations, call by call
+    for (b200_endpoint* ep : seps) rdma_handle_write(ep, nullptr);
+    for (b200_endpoint* ep : reps) rdma_do_read(ep);
+    return;
+  }
+  for (size_t i = 0; i < seps.size(); i++) {
+    b200_endpoint* ep = seps[i];
+    std::string err;
+    if (!finish_flush(ep, acc[i], &err)) notify_on(ep, ep->wr, false);
+    else finish_write(ep, err.empty() ? nullptr : err.c_str());
+  }
+  for (size_t i = 0; i < reps.size(); i++) {
+    b200_endpoint* ep = reps[i];
+    const size_t got = (size_t)del[i];
+    if (got) {
+      ep->inq = e->ops->readable(ep->pair) > 0;
+      // adapt the next read to what this one found (tcp_posix.cc: finish_estimate / target_length)
+      const size_t cap = ep->incoming.empty() ? 0 : ep->incoming[0].len;
+      if (got == cap) ep->target_length = std::min(e->max_read_chunk, std::max<size_t>(2 * cap, 4096));
+      else if (got < cap / 2) ep->target_length = std::max<size_t>(256, cap / 2);
+    }
+    finish_read(ep, got, rlen[i]);
+  }
+}
+
 }  // namespace
 
 // ============================================================ public: engine
@@ -362,17 +569,28 @@ extern "C" b200_engine* b200_engine_create(const b200_pair_ops* ops, int busy_po
   b200_engine* e = new b200_engine();
   e->ops = ops ? ops : &kCudaOps;
   e->epfd = epoll_create1(EPOLL_CLOEXEC);
+  e->wake_fd = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+  struct epoll_event ev;
+  ev.events = (uint32_t)EPOLLIN;
+  ev.data.ptr = reinterpret_cast<void*>(kTagWake);
+  epoll_ctl(e->epfd, EPOLL_CTL_ADD, e->wake_fd, &ev);
   if (busy_poll_us < 0) {
     const char* v = getenv("GRPC_RDMA_BUSY_POLLING_TIMEOUT_US");  // config.cc:75-81
     busy_poll_us = v ? atoi(v) : 500;
   }
   e->busy_poll_us = busy_poll_us;
+  const char* b = getenv("B200_ENDPOINT_BATCH");
+  e->batch = e->ops->submit != nullptr && (!b || atoi(b) != 0);
+  const char* c = getenv("B200_ENDPOINT_READ_CHUNK_KB");
+  if (c && atol(c) > 0) e->max_read_chunk = (size_t)atol(c) * 1024;
+  e->pool = std::make_shared<Pool>(e->ops);
   return e;
 }
 
 extern "C" void b200_engine_destroy(b200_engine* e) {
   if (!e) return;
   if (e->epfd >= 0) close(e->epfd);
+  if (e->wake_fd >= 0) close(e->wake_fd);
   delete e;
 }
 
@@ -380,10 +598,15 @@ extern "C" void b200_engine_stats(b200_engine* e, uint64_t out[4]) {
   Lock lk(e->mu);
   for (int i = 0; i < 4; i++) out[i] = e->stats[i];
 }
-
-// pollable_epoll (:1079-1176) + pollable_process_events (:977-1066)
-extern "C" int b200_engine_work(b200_engine* e, int timeout_ms) {
+extern "C" void b200_engine_batch_stats(b200_engine* e, uint64_t out[3]) {
   Lock lk(e->mu);
+  for (int i = 0; i < 3; i++) out[i] = e->bstats[i];
+}
+
+// pollable_epoll (:1079-1176) + pollable_process_events (:977-1066).  Like the reference (rdma_mu, :1103-1145)
+// the lock is held around one scan of the pairs only: not between scans, not across epoll_wait, not while
+// the GPU works on a submit and not while a user callback runs.
+extern "C" int b200_engine_work(b200_engine* e, int timeout_ms) {
   const b200_pair_ops* ops = e->ops;
   struct Ev {
     b200_endpoint* ep;
@@ -395,26 +618,31 @@ extern "C" int b200_engine_work(b200_engine* e, int timeout_ms) {
   if (timeout_ms >= 0) polling_timeout_us = std::min<int64_t>((int64_t)timeout_ms * 1000, polling_timeout_us);
   const auto begin = std::chrono::steady_clock::now();
   int64_t elapsed_us = 0;
+  bool queued = false;
   do {  // busy-poll window over the pairs (:1104-1145)
-    for (size_t i = 0; i < e->rdma_fds.size() && evs.size() < (size_t)kMaxEpollEvents; i++) {
-      b200_endpoint* ep = e->rdma_fds[i];
-      const int status = ops->status(ep->pair);
-      if (status == B200_CONNECTED) {
-        uint32_t events = 0;
-        if (ops->has_message(ep->pair)) events |= EPOLLIN;
-        if (ops->has_pending_writes(ep->pair)) events |= EPOLLOUT;
-        if (events) evs.push_back({ep, events, false});
-      } else if (status == B200_HALF_CLOSED || status == B200_ERROR) {
-        evs.push_back({ep, EPOLLIN, false});  // so that do_read handles the close
+    {
+      Lock lk(e->mu);
+      for (size_t i = 0; i < e->rdma_fds.size() && evs.size() < (size_t)kMaxEpollEvents; i++) {
+        b200_endpoint* ep = e->rdma_fds[i];
+        const int status = ops->status(ep->pair);
+        if (status == B200_CONNECTED) {
+          uint32_t events = 0;
+          if (ops->has_message(ep->pair)) events |= EPOLLIN;
+          if (ops->has_pending_writes(ep->pair)) events |= EPOLLOUT;
+          if (events) evs.push_back({ep, events, false});
+        } else if (status == B200_HALF_CLOSED || status == B200_ERROR) {
+          evs.push_back({ep, EPOLLIN, false});  // so that do_read handles the close
+        }
       }
+      queued = !e->q_reads.empty() || !e->q_writes.empty() || !e->exec.empty();
     }
     elapsed_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - begin).count();
-  } while (evs.empty() && elapsed_us < polling_timeout_us);
+  } while (evs.empty() && !queued && elapsed_us < polling_timeout_us);
   if (!evs.empty()) {
+    Lock lk(e->mu);
     e->stats[0]++;
     e->stats[2] += evs.size();
-  } else {  // busy-polling timed out: switch to epoll on the pairs' eventfds (:1151-1163)
-    e->stats[1]++;
+  } else if (!queued) {  // busy-polling timed out: switch to epoll on the pairs' eventfds (:1151-1163)
     int timeout = timeout_ms;
     if (timeout > 0) timeout = (int)std::max<int64_t>(0, timeout - elapsed_us / 1000);
     struct epoll_event eev[kMaxEpollEvents];
@@ -423,12 +651,21 @@ extern "C" int b200_engine_work(b200_engine* e, int timeout_ms) {
       r = epoll_wait(e->epfd, eev, kMaxEpollEvents, timeout);
     } while (r < 0 && errno == EINTR);
     if (r < 0) return -1;
+    Lock lk(e->mu);
+    e->stats[1]++;
     for (int i = 0; i < r; i++) {
       const intptr_t tag = reinterpret_cast<intptr_t>(eev[i].data.ptr);
-      if (tag & 2) evs.push_back({reinterpret_cast<b200_endpoint*>(tag & ~(intptr_t)2), eev[i].events, true});
+      if (tag == kTagWake) {
+        eventfd_t v;
+        (void)eventfd_read(e->wake_fd, &v);
+      } else if (tag & kTagPair) {
+        evs.push_back({reinterpret_cast<b200_endpoint*>(tag & ~kTagPair), eev[i].events, true});
+      }
     }
     e->stats[3] += evs.size();
   }
+  Lock lk(e->mu);
+  e->in_work = true;
   for (const Ev& ev : evs) {
     b200_endpoint* ep = ev.ep;
     if (std::find(e->rdma_fds.begin(), e->rdma_fds.end(), ep) == e->rdma_fds.end()) continue;  // orphaned meanwhile
@@ -444,7 +681,15 @@ extern "C" int b200_engine_work(b200_engine* e, int timeout_ms) {
       if (ev.events & (EPOLLOUT | EPOLLHUP)) set_ready(ep, ep->wr, false);
     }
   }
-  flush(e);
+  flush(e, lk);  // closures scheduled meanwhile (errors, call-by-call continuations)
+  if (e->batch) {
+    eventfd_t v;
+    (void)eventfd_read(e->wake_fd, &v);
+    run_batch(e, lk);
+    flush(e, lk);
+  }
+  e->in_work = false;
+  if (!e->q_reads.empty() || !e->q_writes.empty()) kick_engine(e);  // queued by the callbacks: next pass must not sleep
   return (int)evs.size();
 }
 
@@ -517,7 +762,7 @@ extern "C" b200_endpoint* b200_endpoint_create(b200_engine* e, int fd, const cha
   // grpc_fd_set_arg + pollable_add_fd: the pair's eventfd joins the epoll set with tag ptr|2
   struct epoll_event ev;
   ev.events = (uint32_t)(EPOLLIN | EPOLLET);
-  ev.data.ptr = reinterpret_cast<void*>(reinterpret_cast<intptr_t>(ep) | 2);
+  ev.data.ptr = reinterpret_cast<void*>(reinterpret_cast<intptr_t>(ep) | kTagPair);
   epoll_ctl(e->epfd, EPOLL_CTL_ADD, ops->wakeup_read_fd(pair), &ev);
   e->rdma_fds.push_back(ep);
   if (ep->enable_poller) ops->poller_add(pair);  // :790-793
@@ -540,9 +785,9 @@ extern "C" void b200_endpoint_read(b200_endpoint* ep, b200_closure_fn cb, void* 
   } else if (!urgent && ep->inq == 0) {
     notify_on(ep, ep->rd, true);
   } else {
-    schedule(e, [ep] { rdma_handle_read(ep, nullptr); });
+    dispatch(ep, true);
   }
-  flush(e);
+  flush(e, lk);
 }
 
 extern "C" size_t b200_endpoint_incoming(b200_endpoint* ep, const b200_slice** slices) {
@@ -559,31 +804,33 @@ extern "C" void b200_endpoint_write(b200_endpoint* ep, const b200_slice* slices,
   uint64_t length = 0;
   for (size_t i = 0; i < n; i++) length += slices[i].len;
   if (length == 0) {  // :566-574
-    if (ep->shutdown) {
-      std::string es = annotate(ep, "EOF");
-      schedule(e, [cb, arg, es] { cb(arg, es.c_str()); });
-    } else {
-      schedule(e, [cb, arg] { cb(arg, nullptr); });
-    }
-    flush(e);
+    if (ep->shutdown) schedule_user(e, cb, arg, annotate(ep, "EOF").c_str());
+    else schedule_user(e, cb, arg, nullptr);
+    flush(e, lk);
     return;
   }
   ep->outgoing = slices;
   ep->outgoing_count = n;
   ep->outgoing_idx = 0;
   ep->outgoing_byte_idx = 0;
+  if (e->batch) {  // the flush loop runs with everybody else's in the next engine pass
+    ep->refs++;
+    ep->write_cb = cb;
+    ep->write_arg = arg;
+    dispatch(ep, false);
+    flush(e, lk);
+    return;
+  }
   std::string err;
   if (!rdma_flush(ep, &err)) {
     ep->refs++;
     ep->write_cb = cb;
     ep->write_arg = arg;
     notify_on(ep, ep->wr, false);
-  } else if (err.empty()) {
-    schedule(e, [cb, arg] { cb(arg, nullptr); });
   } else {
-    schedule(e, [cb, arg, err] { cb(arg, err.c_str()); });
+    schedule_user(e, cb, arg, err.empty() ? nullptr : err.c_str());
   }
-  flush(e);
+  flush(e, lk);
 }
 
 // rdma_shutdown, rdma_bp_posix.cc:100-104 (grpc_fd_shutdown)
@@ -602,7 +849,7 @@ extern "C" void b200_endpoint_shutdown(b200_endpoint* ep, const char* why) {
     ep->wr.armed = false;
     schedule(e, [ep, es] { rdma_handle_write(ep, es.c_str()); });
   }
-  flush(e);
+  flush(e, lk);
 }
 
 // rdma_destroy, rdma_bp_posix.cc:168 -> RDMA_UNREF

@@ -60,6 +60,16 @@ typedef struct b200_pair_ops {
   void (*disconnect)(void* pair);
   void (*poller_add)(void* pair);
   void (*poller_remove)(void* pair);
+  /* ---- optional (NULL = not provided): the B200-native widening.
+   * submit: one event-loop pass -- every ready Send (rdma_flush loop) and Recv (rdma_do_read loop) posted
+   * together and waited for together (b200_pairs_submit).  When present the engine BATCHES: reads and writes
+   * are queued by rdma_read / rdma_write / the readiness scan and executed by the next b200_engine_work pass.
+   * mem_alloc / mem_free: GPU-addressable memory for the read slices the endpoint allocates itself
+   * (rdma_bp_posix.cc:308-317); they are pooled and 256-byte aligned. */
+  int (*submit)(const b200_send_op* sops, size_t ns, uint64_t* accepted, const b200_recv_op* rops, size_t nr,
+                uint64_t* delivered, int flags);
+  void* (*mem_alloc)(size_t bytes);
+  void (*mem_free)(void* p);
 } b200_pair_ops;
 
 /* NULL ops = libb200rdma.so.  busy_poll_us < 0 = GRPC_RDMA_BUSY_POLLING_TIMEOUT_US (500). */
@@ -72,6 +82,12 @@ int b200_engine_work(b200_engine* e, int timeout_ms);
 /* counters: [0] passes that found work while busy-polling, [1] passes that went to epoll_wait,
  * [2] events synthesized by the scan, [3] eventfd (tag) events */
 void b200_engine_stats(b200_engine* e, uint64_t out[4]);
+/* batching engines: [0] submit calls, [1] Send ops, [2] Recv ops submitted so far */
+void b200_engine_batch_stats(b200_engine* e, uint64_t out[3]);
+/* Threading: any thread may call b200_endpoint_read / write / shutdown / destroy while another one is inside
+ * b200_engine_work (the engine lock is only held while the engine's own state is touched -- never across
+ * epoll_wait, a submit, or a user callback).  Callbacks run on the thread that is in b200_engine_work or in
+ * the call that completed inline. */
 
 /* grpc_rdma_bp_create, rdma_bp_posix.cc:706-796: takes a pair from the pool, Init, exchanges the
  * 48-byte address over the connected socket `fd` (blocking, exchange_data :640), Connect,

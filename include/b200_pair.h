@@ -253,6 +253,13 @@ typedef struct b200_recv_op {
 int b200_pairs_send(const b200_send_op* ops, size_t nops, int flags, uint64_t* accepted, void* stream);
 int b200_pairs_recv(const b200_recv_op* ops, size_t nops, int flags, uint64_t* delivered, void* stream);
 
+/* One event-loop pass: all ready Sends and Recvs posted together, waited for together (what
+ * pollable_process_events does closure by closure, ev_epollex_rdma_bpev_linux.cc:977-1066).  With the service
+ * running nothing is launched: every op is a command of its pair's owner queue, slices (any host memory;
+ * unregistered slices are staged) and destinations (GPU-addressable) are used in place.  0 on success. */
+int b200_pairs_submit(const b200_send_op* sops, size_t ns, uint64_t* accepted, const b200_recv_op* rops, size_t nr,
+                      uint64_t* delivered, int flags);
+
 /* Prepared batches: descriptors uploaded to HBM once, launched many times
  * (streaming workloads that reuse their buffers; CUDA-graph friendly). */
 typedef struct b200_batch b200_batch;

@@ -27,6 +27,8 @@ def load(pkg, need_oracle):
     D.drv_peer_close.argtypes = [C.c_void_p, C.c_int, C.c_int]
     D.drv_echo.restype = C.c_int
     D.drv_echo.argtypes = [C.c_void_p, C.c_int, u64, u64, C.c_int, C.c_int, C.c_int, C.POINTER(u64)]
+    D.drv_two_threads.restype = C.c_int
+    D.drv_two_threads.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(u64)]
     D.drv_multi_echo.restype = C.c_int
     D.drv_multi_echo.argtypes = [C.c_void_p, C.c_int, C.c_int, u64, u64, C.c_int, C.c_int, C.c_int, C.POINTER(u64)]
     ops = None

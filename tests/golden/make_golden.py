@@ -33,6 +33,16 @@ def main():
     with open(path, "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)
     print("wrote", path, os.path.getsize(path), "bytes")
+    # BASELINE-size traces: their own file, no ring images
+    full = {"generator": out["generator"], "max_sge": 30, "ring_images": False, "traces": {}}
+    for name, (cap, ops) in trace.golden_traces_full().items():
+        recs = trace.run_trace(R, cap, ops, ring_images=False)
+        full["traces"][name] = {"cap": cap, "ops": [list(o) for o in ops], "records": recs}
+        print("%-22s cap=%-9d ops=%-3d" % (name, cap, len(ops)))
+    path = os.path.join(HERE, "traces_full.json")
+    with open(path, "w") as f:
+        json.dump(full, f, indent=0, sort_keys=True)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

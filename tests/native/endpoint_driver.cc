@@ -235,6 +235,53 @@ extern "C" int drv_peer_close(const b200_pair_ops* ops, int busy_us, int enable_
   return 0;
 }
 
+// b200_engine_work must not hold the engine lock while it sleeps in epoll_wait (or runs callbacks):
+// a thread inside b200_engine_work(timeout) and another one calling b200_endpoint_write / read on the same
+// engine.  Every call of the second thread has to return long before the first one's wait ends.
+extern "C" int drv_two_threads(const b200_pair_ops* ops, int wait_ms, int rounds, uint64_t* worst_call_us) {
+  Fixture f;
+  if (!make_fixture(ops, 0, 0, false, &f)) FAIL();
+  std::atomic<int> stop{0}, in_work{0};
+  std::thread worker([&] {
+    while (!stop.load()) {
+      in_work = 1;
+      b200_engine_work(f.eng[0], wait_ms);  // busy window 0: goes straight to epoll_wait(wait_ms)
+      in_work = 0;
+    }
+  });
+  uint64_t worst = 0;
+  int rc = 0;
+  Count wc, rcnt;
+  std::vector<uint8_t> block(4096, 0x42);
+  b200_slice sl{block.data(), block.size()};
+  for (int k = 0; k < rounds && !rc; k++) {
+    while (!in_work.load()) {
+    }
+    std::this_thread::sleep_for(std::chrono::milliseconds(2));  // the worker is asleep in epoll_wait now
+    const auto t0 = Clock::now();
+    b200_endpoint_write(f.ep[1], &sl, 1, count_cb, &wc);
+    const auto t1 = Clock::now();
+    b200_endpoint_read(f.ep[0], count_cb, &rcnt, 0);
+    const auto t2 = Clock::now();
+    const uint64_t us = std::chrono::duration_cast<std::chrono::microseconds>(std::max(t1 - t0, t2 - t1)).count();
+    worst = std::max(worst, us);
+    // both complete (the worker thread, or one of our own calls, runs the callbacks)
+    const auto deadline = Clock::now() + std::chrono::seconds(20);
+    while ((wc.ok + wc.fail < k + 1 || rcnt.ok + rcnt.fail < k + 1) && !rc) {
+      if (Clock::now() > deadline) rc = __LINE__;
+      std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+  }
+  stop = 1;
+  worker.join();
+  if (!rc && (wc.fail || rcnt.fail)) rc = __LINE__;
+  if (worst_call_us) *worst_call_us = worst;
+  b200_endpoint_destroy(f.ep[0]);
+  b200_endpoint_destroy(f.ep[1]);
+  drop_fixture(&f);
+  return rc;
+}
+
 namespace {
 
 struct Stream {  // message framing on the byte stream: [u64 length][bytes]

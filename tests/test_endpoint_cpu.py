@@ -96,3 +96,14 @@ def test_many_connections_on_one_engine(drv):
     st = (C.c_uint64 * 4)()
     assert D.drv_multi_echo(ops, 120, 3, 20_000, 99, 50, 0, 0, st) == 0
     assert st[2] >= 120 * 3          # events synthesized by the busy-poll scan
+
+
+def test_engine_lock_is_not_held_across_the_wait(drv):
+    """One thread sleeps inside b200_engine_work(200 ms); another one calls b200_endpoint_write / read on the
+    same engine: the calls return at once (the reference holds rdma_mu only around the pair scan,
+    ev_epollex_rdma_bpev_linux.cc:1103-1145) and both complete."""
+    D, O, ops = drv
+    O.oracle_ops_config(65536, 30)
+    worst = C.c_uint64(0)
+    assert D.drv_two_threads(ops, 200, 5, C.byref(worst)) == 0
+    assert worst.value < 50_000, "a call blocked for %d us behind the sleeping engine" % worst.value

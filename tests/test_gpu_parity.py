@@ -39,6 +39,20 @@ def test_golden_traces_on_gpu(gpu, name, mem, mis):
     _compare(recs, t["records"], "golden %s [%s+%d]" % (name, mem, mis))
 
 
+GOLDEN_FULL = json.load(open(os.path.join(HERE, "golden", "traces_full.json")))
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_FULL["traces"]))
+@pytest.mark.parametrize("mem,mis", [("device", 0), ("pinned", 5)])
+def test_golden_full_size_on_gpu(gpu, name, mem, mis):
+    """The headline configuration against the reference itself: 16 MiB ring, 4 MiB chttp2-shaped messages
+    (514 slices), ring filled to the brim and wrapped more than twice -- every return value, every cursor and
+    the SHA-1 of everything delivered, op by op, as oracle/_ref produced them (tests/golden/make_golden.py)."""
+    t = GOLDEN_FULL["traces"][name]
+    recs = trace.run_trace(GpuEngine(gpu, mem, mis), t["cap"], _ops(t["ops"]), GOLDEN_FULL["max_sge"], ring_images=False)
+    _compare(recs, t["records"], "golden full %s [%s+%d]" % (name, mem, mis))
+
+
 def _random_ops(rng, cap, n_ops):
     ops = []
     for _ in range(n_ops):

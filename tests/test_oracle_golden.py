@@ -31,6 +31,20 @@ def test_oracle_matches_golden(oracle, name):
         assert got == want, "trace %s op %d (%s)" % (name, i, want["op"])
 
 
+GOLDEN_FULL = json.load(open(os.path.join(HERE, "golden", "traces_full.json")))
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_FULL["traces"]))
+def test_oracle_matches_golden_full_size(oracle, name):
+    """BASELINE size: 16 MiB ring, 4 MiB chttp2-shaped messages, the ring wrapped more than twice."""
+    t = GOLDEN_FULL["traces"][name]
+    recs = trace.run_trace(oracle, t["cap"], _ops(t["ops"]), GOLDEN_FULL["max_sge"], ring_images=False)
+    assert len(recs) == len(t["records"])
+    for i, (got, want) in enumerate(zip(recs, t["records"])):
+        assert got == want, "trace %s op %d (%s)" % (name, i, want["op"])
+    assert sum(r["ret"] for r in recs if r["op"] in ("recv", "recv_drain", "stream")) > 2 * t["cap"]
+
+
 def test_golden_covers_required_cases():
     names = set(GOLDEN["traces"])
     for need in ["frame_sizes_64k", "max_frames_4k", "wrap_walk_1k", "partial_reads_1k", "max_sge_cut_64k",

@@ -187,3 +187,24 @@ def golden_traces():
     T["chttp2_300k_128k"] = (131072, [("stream", lens, 21, 50000), ("stream", lens, 22, 1 << 20),
                                       ("stream", [300005], 23, 4096)])
     return T
+
+
+def golden_traces_full():
+    """BASELINE-size fixture: 16 MiB ring, 4 MiB chttp2-shaped messages -- 514 slices each --
+    enough of them that the ring wraps more than twice; the ring filled to the brim (credit exhaustion at full
+    size), drained through single Recv calls and rdma_do_read loops of several sizes.  Replayed without ring
+    images (hashing 16 MiB per op in Python is what would make this slow), every cursor and every delivered
+    byte (SHA-1) per op."""
+    lens = []
+    data = 5 + 4 * 1024 * 1024
+    while data > 0:
+        n = min(16384, data)
+        lens += [9, n]
+        data -= n
+    ops = [("send_all", lens, 400 + k, 0) for k in range(4)]        # the 4th no longer fits: partial write
+    ops += [("recv", 50000), ("recv", 9), ("recv", 16384), ("recv_drain", 1 << 20), ("recv_drain", 3 << 20),
+            ("send_all", lens, 404, 0),                            # credit came back at C/2: room again
+            ("recv_drain", 1 << 25)]                               # everything
+    for k, rcap in enumerate([1 << 20, 5 << 20, 300000, 1 << 22, 1 << 20, 7 << 20, 1 << 16]):
+        ops.append(("stream", lens, 410 + k, rcap))                # closed loops: > 2 more laps of the ring
+    return {"chttp2_4m_16m": (16 * 1024 * 1024, ops)}
