@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-unary", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--no-endpoint", action="store_true", help="skip the e2e_endpoint leg")
+    ap.add_argument("--no-nvlink", action="store_true", help="skip the NVLink-wire integrity pass of N >= 2 runs")
     ap.add_argument("--endpoint-threads", type=int, default=8, help="client/server thread pairs of the endpoint leg")
     ap.add_argument("--endpoint-msgs", type=int, default=16)
     ap.add_argument("--endpoint-pool", type=int, default=128, help="pool CTAs of the service during the endpoint leg")
@@ -448,6 +449,14 @@ def main():
         clocks = dict(e2e["clocks"], note="no sample fell inside the %.0f ms device-resident region; "
                                            "these are the samples of the e2e region that follows it" % ((t_region1 - t_region0) * 1e3))
 
+    # ---- N >= 2: the CUDA-IPC / NVLink wire, exercised in every multi-GPU run (pytest -m gpu on one GPU skips it)
+    nvlink = None
+    if world > 1 and not args.no_nvlink:
+        try:
+            nvlink = run_nvlink_pass(pkg, L, dist, dev, stream, sh, rank, world, args.ring_kb, msg)
+        except Exception as exc:
+            nvlink = {"error": repr(exc)}
+
     unary = None
     if rank == 0 and not args.no_unary:
         for b in (bs, bs2, br):
@@ -497,6 +506,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": e2e,
             "e2e_endpoint": e2e_endpoint,
+            "nvlink_wire": nvlink,
             "unary": unary,
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -507,6 +517,75 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_nvlink_pass(pkg, L, dist, dev, stream, sh, rank, world, ring_kb, msg, conns=64, steps=4):
+    """Connections that CROSS GPUs: rank r's senders are connected to rank (r+1) % N's receivers over the CUDA-IPC
+    wire, so k_send stores its frames into rings in the next GPU's HBM over NVLink and k_recv returns credit the
+    other way.  A short pass with a full integrity check; time = max over ranks."""
+    import torch
+    pkg.config_set("GRPC_RDMA_RING_BUFFER_SIZE_KB", ring_kb)
+    tx = [pkg.Pair("nv-tx-%d-%d" % (rank, c)) for c in range(conns)]
+    rx = [pkg.Pair("nv-rx-%d-%d" % (rank, c)) for c in range(conns)]
+    everyone = [None] * world
+    dist.all_gather_object(everyone, {"tx": [p.address() for p in tx], "rx": [p.address() for p in rx]})
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    for c in range(conns):
+        if not tx[c].connect(everyone[nxt]["rx"][c]) or not rx[c].connect(everyone[prv]["tx"][c]):
+            raise RuntimeError("nvlink wire connect failed: %s / %s" % (tx[c].error(), rx[c].error()))
+    dist.barrier()
+    lens = pkg.chttp2_slice_lens(msg)
+    total = sum(lens)
+    wire_bytes = sum(16 + (n + 7) // 8 * 8 for n in lens)
+    i = torch.arange(total, device=dev, dtype=torch.int64)
+    row = (((i * 2654435761) >> 11) & 255).to(torch.uint8)
+
+    def payload(r, k):
+        offs = (((torch.arange(conns, device=dev, dtype=torch.int64) + r * conns) * 131 + 29 * k) & 255).to(torch.uint8)
+        return (row[None, :] + offs[:, None]).reshape(-1)
+
+    srcs = [payload(rank, 0), payload(rank, 1)]
+    dst = torch.zeros(conns * total, dtype=torch.uint8, device=dev)
+    batches, keep = [], []
+    for src in srcs:
+        sops = []
+        for c in range(conns):
+            off, sl = 0, []
+            for n in lens:
+                sl.append((src.data_ptr() + c * total + off, n))
+                off += n
+            arr = pkg.make_slices(sl)
+            keep.append(arr)
+            sops.append((tx[c], arr, len(lens), 0))
+        batches.append(pkg.Batch("send", sops, pkg.UNTIL_BLOCKED))
+    br = pkg.Batch("recv", [(rx[c], dst.data_ptr() + c * total, total) for c in range(conns)], pkg.UNTIL_BLOCKED)
+    send_ms, ok = [], True
+    for k in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record(stream)
+        batches[k & 1].launch(sh)
+        e1.record(stream)
+        stream.synchronize()
+        dist.barrier()                                          # the neighbour's frames have landed in my rings
+        br.launch(sh)
+        stream.synchronize()
+        ok = ok and batches[k & 1].results(sh) == [total] * conns and br.results(sh) == [total] * conns
+        ok = ok and bool(torch.equal(dst, payload(prv, k & 1)))  # every step carries a different payload
+        if k >= 1:
+            send_ms.append(e0.elapsed_time(e1))
+    t = torch.tensor([sum(send_ms) / max(1, len(send_ms)), 0.0 if ok else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for b in batches + [br]:
+        b.destroy()
+    for p in tx + rx:
+        p.disconnect()
+    dist.barrier()
+    s_ms, bad = t.tolist()
+    return {"what": "k_send over the CUDA-IPC/NVLink wire into the next GPU's rings, k_recv credit back",
+            "connections_per_gpu": conns, "message_bytes": msg, "steps": steps, "intact_all_ranks": bad == 0.0,
+            "k_send_ms": s_ms, "payload_GBps_per_gpu": conns * msg / (s_ms * 1e-3) / 1e9 if s_ms else None,
+            "nvlink_write_GBps_per_gpu": conns * wire_bytes / (s_ms * 1e-3) / 1e9 if s_ms else None}
 
 
 def run_e2e_endpoint(args, pkg, L, with_cpu):

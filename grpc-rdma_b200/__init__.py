@@ -106,6 +106,9 @@ _SIGS = {
     "b200_pairs_recv": (C.c_int, [C.POINTER(RecvOp), C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]),
     "b200_pairs_submit": (C.c_int, [C.POINTER(SendOp), C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(RecvOp), C.c_size_t,
                                     C.POINTER(C.c_uint64), C.c_int]),
+    "b200_pair_post_send": (C.c_void_p, [C.c_void_p, C.POINTER(Slice), C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_int)]),
+    "b200_pair_post_recv": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int)]),
+    "b200_async_poll": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "b200_batch_prepare_send": (C.c_void_p, [C.POINTER(SendOp), C.c_size_t, C.c_int]),
     "b200_batch_prepare_recv": (C.c_void_p, [C.POINTER(RecvOp), C.c_size_t, C.c_int]),
     "b200_batch_launch": (C.c_int, [C.c_void_p, C.c_void_p]),

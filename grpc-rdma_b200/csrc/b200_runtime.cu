@@ -340,6 +340,10 @@ struct TlsBounce {
   uint8_t* tx = nullptr;
   uint8_t* rx = nullptr;
   uint64_t tx_cap = 0, rx_cap = 0;
+  // b200_pairs_submit: device staging of the Recv destinations of one pass + the stream their D2H copies run on
+  uint8_t* dstage = nullptr;
+  uint64_t dstage_cap = 0;
+  cudaStream_t copy_stream = nullptr;
 };
 static std::mutex g_tls_mu;
 static std::vector<TlsBounce*> g_tls_all;
@@ -355,7 +359,19 @@ static TlsBounce& tls_bounce() {
 
 // =================================================================== runtime
 
+static int init_locked(int device);
 extern "C" int b200_init(int device) {
+  const bool was = R().inited;
+  const int rc = init_locked(device);
+  // B200_SERVICE_AUTOSTART=<pool CTAs>: bring the resident service kernels up with the runtime, for programs that
+  // reach this library through the reference-side shim and never call b200_service_start themselves
+  if (rc == 0 && !was) {
+    const long n = env_long("B200_SERVICE_AUTOSTART", 0);
+    if (n > 0 && b200_service_start((int)n) != 0) return -1;
+  }
+  return rc;
+}
+static int init_locked(int device) {
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.mu);
   if (r.inited) return 0;
@@ -466,8 +482,11 @@ extern "C" void b200_shutdown(void) {
     for (TlsBounce* t : g_tls_all) {
       if (t->tx) cudaFreeHost(t->tx);
       if (t->rx) cudaFreeHost(t->rx);
-      t->tx = t->rx = nullptr;
-      t->tx_cap = t->rx_cap = 0;
+      if (t->dstage) cudaFree(t->dstage);
+      if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+      t->tx = t->rx = t->dstage = nullptr;
+      t->copy_stream = nullptr;
+      t->tx_cap = t->rx_cap = t->dstage_cap = 0;
     }
   }
   r.bounce_tx = r.bounce_rx = nullptr;
@@ -1235,12 +1254,18 @@ extern "C" int b200_debug_service_trace(unsigned long long* out16) { return svc_
 // towards total_slice_size (pair.cc:661-664) and is folded into one pseudo-slice that is never dereferenced
 // (SvcCmd.nreal); unregistered memory is staged in the calling thread's pinned bounce buffer
 static bool svc_fill_send(b200_pair* p, SvcCmd* c, SliceDev* area, const b200_slice* slices, size_t n, size_t byte_idx,
-                          uint32_t flags, uint64_t* bounce_cursor = nullptr) {
+                          uint32_t flags, uint64_t* bounce_cursor = nullptr, uint8_t* own_bounce = nullptr,
+                          uint64_t own_bounce_cap = 0) {
   const bool one_call = !(flags & B200_BATCH_UNTIL_BLOCKED);  // (flags >> 16: owed Retire)
   size_t look = n;
   if (one_call && look > (size_t)p->max_sge) look = (size_t)p->max_sge;
   if (look > kSvcSliceArea - 1) look = kSvcSliceArea - 1;
-  TlsBounce& tb = tls_bounce();
+  TlsBounce own;  // an op that outlives the call brings its own staging
+  own.tx = own_bounce;
+  own.tx_cap = own_bounce_cap;
+  uint64_t zero = 0;
+  if (own_bounce && !bounce_cursor) bounce_cursor = &zero;
+  TlsBounce& tb = own_bounce ? own : tls_bounce();
   uint64_t bounce_off = bounce_cursor ? *bounce_cursor : 0;
   // unregistered host memory is staged in the calling thread's pinned buffer like the reference copies
   // into its registered send buffer; what does not fit is left for the next call (the op then ends there)
@@ -1887,6 +1912,37 @@ extern "C" int b200_pairs_submit(const b200_send_op* sops, size_t ns, uint64_t* 
   uint64_t cursor = 0;
   const uint32_t fl = (uint32_t)(flags & (B200_BATCH_UNTIL_BLOCKED));
   int rc = 0;
+  // Optional (B200_SUBMIT_STAGE_MIN=<bytes>, off by default): Recv into pinned HOST destinations of at least that
+  // size goes through device staging and ONE contiguous D2H copy per op by the copy engine instead of SM stores
+  // over PCIe.  (SM-issued PCIe traffic tops out near 50 GB/s for reads and writes TOGETHER, tools/zc_overlap.py;
+  // on the endpoint streaming workload the staged form measured the same as the in-place form.)
+  static const uint64_t kStageMin = (uint64_t)env_long("B200_SUBMIT_STAGE_MIN", 1l << 40);
+  static thread_local std::vector<uint8_t*> rstage;
+  rstage.assign(nr, nullptr);
+  {
+    uint64_t want = 0;
+    for (size_t i = 0; i < nr; i++)
+      if (rops[i].cap >= kStageMin && mem_kind3(rops[i].dst) == 1) want += (rops[i].cap + 255) & ~255ull;
+    if (want) {
+      cudaSetDevice(r.dev);
+      if (want > tb.dstage_cap) {
+        if (tb.dstage) rt_free(tb.dstage, 0);
+        tb.dstage = nullptr;
+        tb.dstage_cap = 0;
+        if (CU_OK(cudaMalloc(&tb.dstage, want))) tb.dstage_cap = want;
+      }
+      if (!tb.copy_stream && !CU_OK(cudaStreamCreateWithFlags(&tb.copy_stream, cudaStreamNonBlocking))) tb.copy_stream = nullptr;
+      if (tb.dstage && tb.copy_stream) {
+        uint64_t off = 0;
+        for (size_t i = 0; i < nr; i++)
+          if (rops[i].cap >= kStageMin && mem_kind3(rops[i].dst) == 1) {
+            rstage[i] = tb.dstage + off;
+            off += (rops[i].cap + 255) & ~255ull;
+          }
+      }
+    }
+  }
+  bool copies = false;
   // answers are collected at the end -- or earlier, when a queue has no free entry: a thread never blocks on
   // a queue while it sits on answers of its own that somebody else's post may be waiting for
   auto harvest = [&]() {
@@ -1904,6 +1960,10 @@ extern "C" int b200_pairs_submit(const b200_send_op* sops, size_t ns, uint64_t* 
       if (!svc_wait(r, rt[i].q, rt[i].t, &bytes, nullptr)) rc = -1;
       rops[i].pair->svc_delivered += bytes;
       if (delivered) delivered[i] = bytes;
+      if (rstage[i] && bytes) {
+        if (!CU_OK(cudaMemcpyAsync(rops[i].dst, rstage[i], bytes, cudaMemcpyDeviceToHost, tb.copy_stream))) rc = -1;
+        copies = true;
+      }
     }
   };
   for (size_t i = 0; i < ns; i++) {
@@ -1951,7 +2011,7 @@ extern "C" int b200_pairs_submit(const b200_send_op* sops, size_t ns, uint64_t* 
       c->op = kSvcRecv;
       c->slot = slot_word(p);
       c->flags = fl;
-      c->ptr = (uint64_t)(uintptr_t)rops[i].dst;
+      c->ptr = (uint64_t)(uintptr_t)(rstage[i] ? rstage[i] : (uint8_t*)rops[i].dst);
       c->n = rops[i].cap;
       c->byte_idx = 0;
     };
@@ -1960,7 +2020,248 @@ extern "C" int b200_pairs_submit(const b200_send_op* sops, size_t ns, uint64_t* 
     rt[i].posted = true;
   }
   harvest();
+  if (copies && !CU_OK(cudaStreamSynchronize(tb.copy_stream))) rc = -1;
   return rc;
+}
+
+// ------------------------------------------------------------------ post / poll (completion-queue form)
+
+struct b200_async {
+  int kind = 0;          // 0 send, 1 recv
+  b200_pair* p = nullptr;
+  int q = 0;
+  uint64_t t = 0;
+  int state = 0;         // 0 posted, 1 copying down, 2 done
+  uint64_t bytes = 0;
+  uint8_t* stage = nullptr;
+  int stage_cls = -1;
+  uint8_t* hstage = nullptr;  // send: pinned staging of unregistered slices, owned until the op has finished
+  int hstage_cls = -1;
+  void* dst = nullptr;
+  cudaEvent_t ev = nullptr;
+};
+
+namespace {
+// device staging blocks of the asynchronous Recvs (power-of-two classes) and finished handles, recycled
+struct AsyncPool {
+  std::mutex mu;
+  std::vector<uint8_t*> free_stage[32], free_hstage[32];
+  std::vector<b200_async*> free_ops;
+  cudaStream_t copy[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::atomic<uint32_t> rr{0};
+};
+AsyncPool& AP() {
+  static AsyncPool a;
+  return a;
+}
+b200_async* async_get() {
+  AsyncPool& a = AP();
+  {
+    std::lock_guard<std::mutex> lk(a.mu);
+    if (!a.free_ops.empty()) {
+      b200_async* o = a.free_ops.back();
+      a.free_ops.pop_back();
+      return o;
+    }
+  }
+  b200_async* o = new b200_async();
+  cudaEventCreateWithFlags(&o->ev, cudaEventDisableTiming);
+  return o;
+}
+void async_put(b200_async* o) {
+  AsyncPool& a = AP();
+  std::lock_guard<std::mutex> lk(a.mu);
+  if (o->stage) a.free_stage[o->stage_cls].push_back(o->stage);
+  if (o->hstage) a.free_hstage[o->hstage_cls].push_back(o->hstage);
+  o->stage = o->hstage = nullptr;
+  o->stage_cls = o->hstage_cls = -1;
+  o->state = 0;
+  a.free_ops.push_back(o);
+}
+uint8_t* stage_get(uint64_t bytes, int* cls) {
+  int c = 16;  // 64 KiB
+  while ((1ull << c) < bytes) c++;
+  *cls = c;
+  AsyncPool& a = AP();
+  {
+    std::lock_guard<std::mutex> lk(a.mu);
+    if (!a.free_stage[c].empty()) {
+      uint8_t* p = a.free_stage[c].back();
+      a.free_stage[c].pop_back();
+      return p;
+    }
+  }
+  uint8_t* p = nullptr;
+  cudaSetDevice(R().dev);
+  if (cudaMalloc(&p, 1ull << c) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+}  // namespace
+
+extern "C" b200_async* b200_pair_post_send(b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx, int flags,
+                                           int* again) {
+  if (again) *again = 0;
+  Runtime& r = R();
+  if (!p || !r.svc_running.load()) {
+    set_err("b200_pair_post_send: the service is not running");
+    return nullptr;
+  }
+  b200_async* o = async_get();
+  o->kind = 0;
+  o->p = p;
+  o->bytes = 0;
+  o->state = 2;  // finished with 0 bytes unless something is posted
+  if (p->status != B200_CONNECTED || n == 0 || ((volatile PairMirror*)p->mirror)->peer_exit == 1) return o;
+  if (p->peer_local) drain_retire(p->peer_local);
+  if (send_is_a_no_op(p)) return o;
+  const int q = owner_of(r, p);
+  bool ok = true;
+  uint64_t t = 0;
+  {  // unregistered slices are staged in pinned memory that belongs to the op
+    uint64_t need = 0;
+    for (size_t i = 0; i < n && i < kSvcSliceArea; i++)
+      if (slices[i].len && mem_kind(slices[i].ptr) == 0) need += (slices[i].len + 15) & ~15ull;
+    if (need) {
+      int c = 12;
+      while ((1ull << c) < need && c < 28) c++;
+      AsyncPool& a = AP();
+      {
+        std::lock_guard<std::mutex> lk(a.mu);
+        if (!a.free_hstage[c].empty()) {
+          o->hstage = a.free_hstage[c].back();
+          a.free_hstage[c].pop_back();
+        }
+      }
+      if (!o->hstage && cudaHostAlloc((void**)&o->hstage, 1ull << c, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        o->hstage = nullptr;
+      }
+      o->hstage_cls = c;
+      if (!o->hstage) {
+        set_err("b200_pair_post_send: pinned staging allocation failed");
+        async_put(o);
+        return nullptr;
+      }
+    }
+  }
+  auto fill = [&](SvcCmd* c, SliceDev* area) {
+    const uint32_t owed = p->retire_owed.exchange(0, std::memory_order_acq_rel);
+    ok = svc_fill_send(p, c, area, slices, n, byte_idx, (uint32_t)(flags & B200_BATCH_UNTIL_BLOCKED) | (owed << 16), nullptr,
+                       o->hstage, o->hstage ? 1ull << o->hstage_cls : 0);
+    if (!ok) {
+      c->op = owed ? kSvcRetire : kSvcNop;
+      c->slot = slot_word(p);
+      c->flags = B200_BATCH_ONE_CALL;
+      c->n = owed;
+    }
+  };
+  if (!svc_try_post(r, q, fill, &t)) {
+    async_put(o);
+    if (again) *again = 1;
+    return nullptr;
+  }
+  o->q = q;
+  o->t = t;
+  o->state = 0;
+  return o;
+}
+
+extern "C" b200_async* b200_pair_post_recv(b200_pair* p, void* dst, uint64_t cap, int flags, int* again) {
+  if (again) *again = 0;
+  Runtime& r = R();
+  if (!p || !r.svc_running.load()) {
+    set_err("b200_pair_post_recv: the service is not running");
+    return nullptr;
+  }
+  b200_async* o = async_get();
+  o->kind = 1;
+  o->p = p;
+  o->bytes = 0;
+  o->dst = dst;
+  o->state = 2;
+  if (p->status != B200_CONNECTED || cap == 0) return o;
+  drain_retire(p);
+  if (!p->remote && ((volatile PairMirror*)p->mirror)->has_message == 0) return o;
+  const int kind = mem_kind3(dst);
+  if (kind == 0) {
+    set_err("b200_pair_post_recv: the destination must be GPU-addressable (b200_mem_alloc_host / register_host / device)");
+    async_put(o);
+    return nullptr;
+  }
+  static const uint64_t kStageMin = (uint64_t)env_long("B200_SUBMIT_STAGE_MIN", 1l << 40);
+  if (kind == 1 && cap >= kStageMin) {
+    o->stage = stage_get(cap, &o->stage_cls);
+    if (!o->stage) o->stage_cls = -1;
+  }
+  const int q = owner_of(r, p);
+  uint64_t t = 0;
+  auto fill = [&](SvcCmd* c, SliceDev*) {
+    c->op = kSvcRecv;
+    c->slot = slot_word(p);
+    c->flags = (uint32_t)(flags & B200_BATCH_UNTIL_BLOCKED);
+    c->ptr = (uint64_t)(uintptr_t)(o->stage ? o->stage : (uint8_t*)dst);
+    c->n = cap;
+    c->byte_idx = 0;
+  };
+  if (!svc_try_post(r, q, fill, &t)) {
+    async_put(o);
+    if (again) *again = 1;
+    return nullptr;
+  }
+  o->q = q;
+  o->t = t;
+  o->state = 0;
+  return o;
+}
+
+extern "C" int b200_async_poll(b200_async* o, uint64_t* bytes) {
+  if (!o) return -1;
+  Runtime& r = R();
+  if (o->state == 0) {
+    const size_t e = (size_t)o->q * kOwnQ + o->t % kOwnQ;
+    volatile SvcDone* d = &r.svc_done[e];
+    if (d->seq != (uint32_t)(o->t + 1)) return 0;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    o->bytes = d->bytes;
+    r.svc_consumed[e].store((uint32_t)(o->t + 1), std::memory_order_release);
+    r.svc_ops++;
+    if (o->kind == 1) {
+      o->p->svc_delivered += o->bytes;
+      if (o->stage && o->bytes) {  // the copy engine takes the delivered bytes down
+        AsyncPool& a = AP();
+        const uint32_t k = a.rr++ & 3;
+        {
+          std::lock_guard<std::mutex> lk(a.mu);
+          if (!a.copy[k]) cudaStreamCreateWithFlags(&a.copy[k], cudaStreamNonBlocking);
+        }
+        if (cudaMemcpyAsync(o->dst, o->stage, o->bytes, cudaMemcpyDeviceToHost, a.copy[k]) != cudaSuccess ||
+            cudaEventRecord(o->ev, a.copy[k]) != cudaSuccess) {
+          cudaGetLastError();
+          async_put(o);
+          return -1;
+        }
+        o->state = 1;
+        return 0;
+      }
+    }
+    o->state = 2;
+  }
+  if (o->state == 1) {
+    const cudaError_t e = cudaEventQuery(o->ev);
+    if (e == cudaErrorNotReady) return 0;
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      async_put(o);
+      return -1;
+    }
+    o->state = 2;
+  }
+  if (bytes) *bytes = o->bytes;
+  async_put(o);
+  return 1;
 }
 
 // ================================================================ calibration

@@ -63,12 +63,27 @@ int d_submit(const b200_send_op* s, size_t ns, uint64_t* acc, const b200_recv_op
   if (!b200_service_running()) return 1;
   return b200_pairs_submit(s, ns, acc, r, nr, del, flags);
 }
+void* d_post_send(void* p, const b200_slice* s, size_t n, size_t b, int flags, int* again) {
+  if (!b200_service_running()) {
+    *again = 2;
+    return nullptr;
+  }
+  return b200_pair_post_send((b200_pair*)p, s, n, b, flags, again);
+}
+void* d_post_recv(void* p, void* dst, uint64_t cap, int flags, int* again) {
+  if (!b200_service_running()) {
+    *again = 2;
+    return nullptr;
+  }
+  return b200_pair_post_recv((b200_pair*)p, dst, cap, flags, again);
+}
+int d_poll(void* op, uint64_t* bytes) { return b200_async_poll((b200_async*)op, bytes); }
 void* d_malloc(size_t n) { return b200_mem_alloc_host(n); }
 void d_mfree(void* p) { b200_mem_free_host(p); }
 const b200_pair_ops kCudaOps = {d_take,   d_putback, d_init,       d_addr,     d_connect, d_send,
                                 d_recv,   d_has_msg, d_pending,    d_readable, d_status,  d_error,
                                 d_wfd,    d_consume, d_disconnect, d_padd,     d_premove, d_submit,
-                                d_malloc, d_mfree};
+                                d_malloc, d_mfree,   d_post_send,  d_post_recv, d_poll};
 
 // Pool of read-slice blocks: power-of-two size classes from 256 bytes, GPU-addressable when the ops table
 // provides an allocator (every b200_mem_alloc_host block is 256-byte aligned: the alignment the PCIe DMA
@@ -193,6 +208,14 @@ struct b200_engine {
   bool in_work = false;  // a thread is between the end of its wait and the end of its pass
   size_t max_read_chunk = 4u << 20;
   std::vector<b200_endpoint*> q_reads, q_writes;  // batching: rdma_do_read / rdma_flush loops to run
+  struct InFlight {
+    b200_endpoint* ep;
+    bool is_read;
+    void* op;
+    size_t rlen;
+  };
+  std::vector<InFlight> inflight;  // completion-queue form: posted, not finished yet
+  bool async = false;
   std::shared_ptr<Pool> pool;
   uint64_t stats[4] = {0, 0, 0, 0};
   uint64_t bstats[3] = {0, 0, 0};
@@ -491,6 +514,9 @@ void ep_unref(b200_endpoint* ep) {
   if (--ep->refs == 0) ep_free(ep);
 }
 
+void complete_write(b200_endpoint* ep, uint64_t accepted);
+void complete_read(b200_endpoint* ep, size_t got, size_t rlen);
+
 // Batching: every queued rdma_flush loop and rdma_do_read loop of this pass in ONE submit.  The lock is
 // released while the GPU works; the queued endpoints are kept alive by the reference their pending
 // read / write holds.
@@ -541,24 +567,100 @@ void run_batch(b200_engine* e, Lock& lk) {
     for (b200_endpoint* ep : reps) rdma_do_read(ep);
     return;
   }
-  for (size_t i = 0; i < seps.size(); i++) {
-    b200_endpoint* ep = seps[i];
-    std::string err;
-    if (!finish_flush(ep, acc[i], &err)) notify_on(ep, ep->wr, false);
-    else finish_write(ep, err.empty() ? nullptr : err.c_str());
+  for (size_t i = 0; i < seps.size(); i++) complete_write(seps[i], acc[i]);
+  for (size_t i = 0; i < reps.size(); i++) complete_read(reps[i], (size_t)del[i], rlen[i]);
+}
+
+void complete_write(b200_endpoint* ep, uint64_t accepted) {
+  std::string err;
+  if (!finish_flush(ep, accepted, &err)) notify_on(ep, ep->wr, false);
+  else finish_write(ep, err.empty() ? nullptr : err.c_str());
+}
+void complete_read(b200_endpoint* ep, size_t got, size_t rlen) {
+  b200_engine* e = ep->engine;
+  if (got) {
+    ep->inq = e->ops->readable(ep->pair) > 0;
+    // adapt the next read to what this one found (tcp_posix.cc: finish_estimate / target_length)
+    const size_t cap = ep->incoming.empty() ? 0 : ep->incoming[0].len;
+    if (got == cap) ep->target_length = std::min(e->max_read_chunk, std::max<size_t>(2 * cap, 4096));
+    else if (got < cap / 2) ep->target_length = std::max<size_t>(256, cap / 2);
   }
-  for (size_t i = 0; i < reps.size(); i++) {
-    b200_endpoint* ep = reps[i];
-    const size_t got = (size_t)del[i];
-    if (got) {
-      ep->inq = e->ops->readable(ep->pair) > 0;
-      // adapt the next read to what this one found (tcp_posix.cc: finish_estimate / target_length)
-      const size_t cap = ep->incoming.empty() ? 0 : ep->incoming[0].len;
-      if (got == cap) ep->target_length = std::min(e->max_read_chunk, std::max<size_t>(2 * cap, 4096));
-      else if (got < cap / 2) ep->target_length = std::max<size_t>(256, cap / 2);
+  finish_read(ep, got, rlen);
+}
+
+// Completion-queue form of run_batch: poll what is in flight, post what is queued; never waits for the GPU.
+// Returns false when posting is not available right now (no service): the caller runs the batch path.
+bool pump(b200_engine* e) {
+  const b200_pair_ops* ops = e->ops;
+  for (size_t i = 0; i < e->inflight.size();) {
+    b200_engine::InFlight f = e->inflight[i];
+    uint64_t bytes = 0;
+    const int r = ops->poll(f.op, &bytes);
+    if (r == 0) {
+      i++;
+      continue;
     }
-    finish_read(ep, got, rlen[i]);
+    e->inflight[i] = e->inflight.back();
+    e->inflight.pop_back();
+    if (r < 0) bytes = 0;
+    if (f.is_read) complete_read(f.ep, (size_t)bytes, f.rlen);
+    else complete_write(f.ep, bytes);
   }
+  if (e->q_reads.empty() && e->q_writes.empty()) return true;
+  std::vector<b200_endpoint*> reads, writes;
+  reads.swap(e->q_reads);
+  writes.swap(e->q_writes);
+  bool available = true;
+  for (size_t k = 0; k < writes.size(); k++) {
+    b200_endpoint* ep = writes[k];
+    if (!ep->write_cb) {
+      ep->queued_write = false;
+      continue;
+    }
+    int again = 0;
+    void* op = available ? ops->post_send(ep->pair, ep->outgoing + ep->outgoing_idx, ep->outgoing_count - ep->outgoing_idx,
+                                          ep->outgoing_byte_idx, B200_BATCH_UNTIL_BLOCKED, &again)
+                         : nullptr;
+    if (op) {
+      ep->queued_write = false;
+      e->inflight.push_back({ep, false, op, 0});
+      e->bstats[1]++;
+    } else if (!available || again) {
+      if (again == 2) available = false;
+      e->q_writes.push_back(ep);  // stays queued
+    } else {
+      ep->queued_write = false;
+      complete_write(ep, 0);
+    }
+  }
+  for (size_t k = 0; k < reads.size(); k++) {
+    b200_endpoint* ep = reads[k];
+    if (!ep->read_cb) {
+      ep->queued_read = false;
+      continue;
+    }
+    int again = 0;
+    void* op = nullptr;
+    if (available) {
+      prepare_read_slice(ep);
+      ep->inq = 1;
+      op = ops->post_recv(ep->pair, ep->incoming.empty() ? nullptr : ep->incoming[0].ptr(),
+                          ep->incoming.empty() ? 0 : ep->incoming[0].len, B200_BATCH_UNTIL_BLOCKED, &again);
+    }
+    if (op) {
+      ep->queued_read = false;
+      e->inflight.push_back({ep, true, op, buf_length(ep->incoming)});
+      e->bstats[2]++;
+    } else if (!available || again) {
+      if (again == 2) available = false;
+      e->q_reads.push_back(ep);
+    } else {
+      ep->queued_read = false;
+      complete_read(ep, 0, buf_length(ep->incoming));
+    }
+  }
+  if (available) e->bstats[0]++;
+  return available;
 }
 
 }  // namespace
@@ -581,6 +683,10 @@ extern "C" b200_engine* b200_engine_create(const b200_pair_ops* ops, int busy_po
   e->busy_poll_us = busy_poll_us;
   const char* b = getenv("B200_ENDPOINT_BATCH");
   e->batch = e->ops->submit != nullptr && (!b || atoi(b) != 0);
+  const char* a = getenv("B200_ENDPOINT_ASYNC");
+  // off by default: measured slower than the pass-at-a-time form on the streaming workload (reads get posted as
+  // soon as the first frames land and come back small; profiles/r2_endpoint_stream.md)
+  e->async = e->batch && e->ops->post_send && e->ops->post_recv && e->ops->poll && a && atoi(a) != 0;
   const char* c = getenv("B200_ENDPOINT_READ_CHUNK_KB");
   if (c && atol(c) > 0) e->max_read_chunk = (size_t)atol(c) * 1024;
   e->pool = std::make_shared<Pool>(e->ops);
@@ -634,7 +740,7 @@ extern "C" int b200_engine_work(b200_engine* e, int timeout_ms) {
           evs.push_back({ep, EPOLLIN, false});  // so that do_read handles the close
         }
       }
-      queued = !e->q_reads.empty() || !e->q_writes.empty() || !e->exec.empty();
+      queued = !e->q_reads.empty() || !e->q_writes.empty() || !e->exec.empty() || !e->inflight.empty();
     }
     elapsed_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - begin).count();
   } while (evs.empty() && !queued && elapsed_us < polling_timeout_us);
@@ -685,7 +791,7 @@ extern "C" int b200_engine_work(b200_engine* e, int timeout_ms) {
   if (e->batch) {
     eventfd_t v;
     (void)eventfd_read(e->wake_fd, &v);
-    run_batch(e, lk);
+    if (!e->async || !pump(e)) run_batch(e, lk);
     flush(e, lk);
   }
   e->in_work = false;

@@ -70,6 +70,12 @@ typedef struct b200_pair_ops {
                 uint64_t* delivered, int flags);
   void* (*mem_alloc)(size_t bytes);
   void (*mem_free)(void* p);
+  /* completion-queue form (b200_pair_post_send / post_recv / b200_async_poll): when present the engine never
+   * waits for the GPU -- each pass polls what is in flight and posts what is queued.  post returns NULL with
+   * *again = 1 (no free queue entry: retry next pass), 2 (not available right now: run call by call), 0 (error). */
+  void* (*post_send)(void* pair, const b200_slice* slices, size_t n, size_t byte_idx, int flags, int* again);
+  void* (*post_recv)(void* pair, void* dst, uint64_t cap, int flags, int* again);
+  int (*poll)(void* op, uint64_t* bytes);
 } b200_pair_ops;
 
 /* NULL ops = libb200rdma.so.  busy_poll_us < 0 = GRPC_RDMA_BUSY_POLLING_TIMEOUT_US (500). */

@@ -260,6 +260,17 @@ int b200_pairs_recv(const b200_recv_op* ops, size_t nops, int flags, uint64_t* d
 int b200_pairs_submit(const b200_send_op* sops, size_t ns, uint64_t* accepted, const b200_recv_op* rops, size_t nr,
                       uint64_t* delivered, int flags);
 
+/* Completion-queue form of the same (service running only): post now, poll later -- the event loop never waits
+ * for the GPU, every connection advances at its own pace.  A posted op is an rdma_flush loop / rdma_do_read loop
+ * (B200_BATCH_UNTIL_BLOCKED) or a single call.  Recv into pinned HOST memory is delivered into device staging and
+ * taken down by the copy engine (one contiguous copy); the op completes when the bytes are in `dst`.
+ * post: NULL + *again = 1 when the pair's command queue has no free entry right now (poll something, post later);
+ *       NULL + *again = 0 on error.  poll: 1 = finished (bytes valid, handle released), 0 = still running, -1 = error. */
+typedef struct b200_async b200_async;
+b200_async* b200_pair_post_send(b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx, int flags, int* again);
+b200_async* b200_pair_post_recv(b200_pair* p, void* dst, uint64_t cap, int flags, int* again);
+int b200_async_poll(b200_async* op, uint64_t* bytes);
+
 /* Prepared batches: descriptors uploaded to HBM once, launched many times
  * (streaming workloads that reuse their buffers; CUDA-graph friendly). */
 typedef struct b200_batch b200_batch;
