@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <fcntl.h>
+#include <signal.h>
 #include <sys/eventfd.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -95,6 +96,8 @@ struct b200_pair {
   uint64_t* remote_credit = nullptr;
   std::string wire_file;  // this pair's descriptor under /dev/shm (unlinked on Disconnect)
   bool in_poller = false;
+  int peer_pid = 0;  // nvlink wire: the process that owns the peer; probed every 500 ms by get_status
+  std::chrono::steady_clock::time_point last_probe{};
   int max_sge = 30;  // captured at Init (what the kernels use for this pair)
   // service: payload bytes Recv has returned since the service started (the device keeps the same count;
   // an eagerly pushed frame is valid only while both agree), and the asynchronous Retire of the last
@@ -303,6 +306,7 @@ struct WireDesc {
   int32_t dev, slot;
   uint64_t cap;
   cudaIpcMemHandle_t ring, pairs;
+  int32_t pid, _pad;  // owner process: the survivor's liveness probe (get_status, pair.cc:358-372)
 };
 constexpr uint32_t kWireMagic = 0xB2001BC0u;
 std::string wire_path(uint32_t cookie, uint32_t qpn) {
@@ -721,6 +725,7 @@ extern "C" void b200_pair_init(b200_pair* p) {
     d.dev = r.dev;
     d.slot = p->slot;
     d.cap = cap;
+    d.pid = (int32_t)getpid();
     d.pairs = r.pairs_handle;
     if (CU_OK(cudaIpcGetMemHandle(&d.ring, p->ring))) {
       p->wire_file = wire_path(r.cookie, p->self.qpn);
@@ -819,6 +824,7 @@ extern "C" int b200_pair_connect(b200_pair* p, const void* peer48, size_t n) {
       return 0;
     }
     p->remote = true;
+    p->peer_pid = d.pid;
     p->remote_ring = (uint8_t*)rring;
     p->remote_credit = hd.peer_credit;
     p->peer_local = nullptr;
@@ -924,6 +930,17 @@ static void refresh_remote(const b200_pair* cp) {
 
 extern "C" enum b200_status b200_pair_status(b200_pair* p) {
   if (!p) return B200_UNINITIALIZED;
+  if (p->remote && p->status == B200_CONNECTED && p->peer_pid > 0) {
+    // the liveness leg of get_status (pair.cc:358-372: ibv_query_qp every 500 ms, anything but RTS -> HalfClosed).
+    // On the CUDA-IPC wire there is no QP to ask: the owner process of the peer pair is probed instead -- a peer
+    // that died without Disconnect (no peer_exit write) leaves nobody to answer, and the survivor must not stay
+    // Connected forever.
+    const auto now = std::chrono::steady_clock::now();
+    if (now - p->last_probe > std::chrono::milliseconds(500)) {
+      p->last_probe = now;
+      if (kill((pid_t)p->peer_pid, 0) != 0 && errno == ESRCH) ((volatile PairMirror*)p->mirror)->peer_exit = 1;
+    }
+  }
   refresh_remote(p);
   if (p->status == B200_CONNECTED && ((volatile PairMirror*)p->mirror)->peer_exit == 1)
     return B200_HALF_CLOSED;  // pair.cc:354-356
@@ -2375,8 +2392,7 @@ extern "C" void b200_poller_add(b200_pair* p) {
   Runtime& r = R();
   std::lock_guard<std::mutex> lk(r.pmu);
   if ((int)r.pollables.size() >= B200_POLLER_CAPACITY) return;  // poller.cc:13 asserts
-  for (b200_pair* q : r.pollables)
-    if (q == p) return;
+  if (p->in_poller) return;  // (O(1): 4096 connections register one after the other)
   r.pollables.push_back(p);
   p->in_poller = true;
   if (!r.poll_running.load()) {

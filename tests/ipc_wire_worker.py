@@ -51,6 +51,18 @@ def main():
         put_file(os.path.join(d, "%s%d.addr" % (me, c)), p.address())
     for c, p in enumerate(pairs):
         assert p.connect(wait_file(os.path.join(d, "%s%d.addr" % (other, c)))), p.error()
+    if os.environ.get("IPC_WIRE_MODE") == "death":
+        # liveness: the server dies without Disconnect right after connecting; the client must see HALF_CLOSED
+        if role == "server":
+            wait_file(os.path.join(d, "client.connected"))
+            os._exit(0)
+        put_file(os.path.join(d, "client.connected"), b"1")
+        t0 = time.time()
+        while pairs[0].status() != 3 and time.time() - t0 < 20:
+            time.sleep(0.05)
+        put_file(os.path.join(d, "client.json"), json.dumps({"half_closed": pairs[0].status() == 3,
+                                                            "seconds": time.time() - t0}).encode())
+        os._exit(0)
     lens = pkg.chttp2_slice_lens(msg)
     total = sum(lens)
     res = {"role": role, "ok": True, "conns": conns}

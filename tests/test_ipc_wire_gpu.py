@@ -37,3 +37,18 @@ def test_stream_across_two_gpus():
 def test_message_larger_than_the_ring_needs_credit_over_nvlink():
     cli, srv = _run(256, 3 << 20, 2, 1)           # 3 MiB messages through a 256 KiB ring
     assert srv["ok"] and srv["ring_empty"] and srv["half_closed"]
+
+
+def test_dead_peer_process_is_detected():
+    """The liveness leg of get_status (pair.cc:358-372): a peer process that dies without Disconnect leaves no
+    peer_exit write behind; the survivor's status probe (every 500 ms) turns the pair HALF_CLOSED.  Both processes
+    share GPU 0, so this also runs on a one-GPU box."""
+    with tempfile.TemporaryDirectory() as d:
+        env = dict(os.environ, IPC_WIRE_MODE="death")
+        procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "ipc_wire_worker.py"), role, "0", d, "64", "1024", "1", "1"],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+                 for role in ("server", "client")]
+        outs = [p.communicate(timeout=200)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+        res = json.load(open(os.path.join(d, "client.json")))
+        assert res["half_closed"] and res["seconds"] < 10, res

@@ -35,8 +35,13 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 numa = bench.bind_to_gpu_numa(local)
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
+cpu_group = None
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+    # reductions / barriers WHILE THE SERVICE RUNS go over gloo on CPU tensors: a first-time CUDA kernel launch
+    # (NCCL's or torch's) loads its module lazily, and that load can wait for an idle device -- which never comes
+    # beside resident kernels
+    cpu_group = dist.new_group(backend="gloo")
 pkg = ge.load_package()
 L = pkg.lib()
 pkg.init(local)
@@ -51,50 +56,38 @@ PP.b200_pp_run.restype = C.c_double
 PP.b200_pp_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint64)]
 
 
+T0 = time.time()
+
+
+def log(*a):
+    if rank == 0:
+        print("[config45 %.1fs]" % (time.time() - T0), *a, file=sys.stderr, flush=True)
+
+
 def allsum(x):
     if world == 1:
         return x
-    t = torch.tensor([x], device=dev, dtype=torch.float64)
-    dist.all_reduce(t)
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, group=cpu_group)
     return float(t.item())
 
 
 def allmax(x):
     if world == 1:
         return x
-    t = torch.tensor([x], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=cpu_group)
     return float(t.item())
 
 
 def barrier():
+    # NOT dist.barrier(): its wait ends in a device-wide synchronisation, which never returns while the resident
+    # service kernels run; an all_reduce + .item() only waits for its own stream
     if world > 1:
-        dist.barrier()
+        allsum(0.0)
 
 
 out = {"n_gpus": world, "numa": numa}
-assert L.b200_service_start(96) == 0, pkg.last_error()
-
-# ------------------------------------------------------------------ configs[3]
-conns4 = max(1, 256 // world)
-sweep = []
-sizes = [1024, 4096, 16384, 65536, 262144, 1 << 20, 4 << 20, 16 << 20]
-for m in sizes:
-    budget = (1 << 26) if quick else (1 << 28)                   # payload bytes per connection
-    msgs = int(max(4, min(2000, budget // m)))
-    o = (C.c_uint64 * 4)()
-    barrier()
-    t = ES.ep_stream_run(None, conns4, min(4, conns4), msgs, 2, m, 0, o)
-    ok = t > 0 and o[1] == 0
-    gbs = o[0] / t / 1e9 if t > 0 else 0.0
-    row = {"message_bytes": m, "connections_per_gpu": conns4, "msgs_per_connection": msgs,
-           "GBps_all_gpus": allsum(gbs), "msgs_per_s_all_gpus": allsum(conns4 * msgs / t if t > 0 else 0.0),
-           "slowest_rank_s": allmax(t), "intact_all_ranks": allsum(0.0 if ok else 1.0) == 0.0}
-    if m > (8 << 20):
-        row["note"] = "message > ring (16 MiB - 24) and > staging (8 MiB): partial writes + C/2 credit returns, rounds driven from C"
-    sweep.append(row)
-out["config4_sweep_through_endpoint"] = sweep
-
 # request fan-out (NCCL all_to_all over NVLink): a quarter of the deframed requests belong to another GPU
 if world > 1:
     import importlib
@@ -125,6 +118,31 @@ if world > 1:
                      "received_here": len(got)})
         del payload, reqs, got
     out["config4_fanout_nccl"] = rows
+    log("fanout done")
+
+assert L.b200_service_start(96) == 0, pkg.last_error()
+log("service up")
+
+# ------------------------------------------------------------------ configs[3]
+conns4 = max(1, 256 // world)
+sweep = []
+sizes = [1024, 4096, 16384, 65536, 262144, 1 << 20, 4 << 20, 16 << 20]
+for m in sizes:
+    budget = (1 << 26) if quick else (1 << 28)                   # payload bytes per connection
+    msgs = int(max(4, min(2000, budget // m)))
+    o = (C.c_uint64 * 4)()
+    barrier()
+    t = ES.ep_stream_run(None, conns4, min(4, conns4), msgs, 2, m, 0, o)
+    ok = t > 0 and o[1] == 0
+    gbs = o[0] / t / 1e9 if t > 0 else 0.0
+    row = {"message_bytes": m, "connections_per_gpu": conns4, "msgs_per_connection": msgs,
+           "GBps_all_gpus": allsum(gbs), "msgs_per_s_all_gpus": allsum(conns4 * msgs / t if t > 0 else 0.0),
+           "slowest_rank_s": allmax(t), "intact_all_ranks": allsum(0.0 if ok else 1.0) == 0.0}
+    if m > (8 << 20):
+        row["note"] = "message > ring (16 MiB - 24) and > staging (8 MiB): partial writes + C/2 credit returns, rounds driven from C"
+    sweep.append(row)
+    log("sweep", m, "->", round(row["GBps_all_gpus"], 2), "GB/s", round(row["msgs_per_s_all_gpus"]), "msgs/s", "t", round(t, 3))
+out["config4_sweep_through_endpoint"] = sweep
 
 # ------------------------------------------------------------------ configs[4]
 conns5 = 128 if quick else 256                                   # unary and streaming each, per GPU
@@ -151,6 +169,7 @@ for x in th:
     x.start()
 for x in th:
     x.join()
+log("config5 gpu part done", res)
 out["config5_mixed"] = {
     "connections_per_gpu": 2 * conns5, "connections_total": 2 * conns5 * world,
     "unary_p50_us_worst_rank": allmax(res["unary"]["p50"]), "unary_p99_us_worst_rank": allmax(res["unary"]["p99"]),
