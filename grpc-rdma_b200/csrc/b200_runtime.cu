@@ -97,6 +97,7 @@ struct b200_pair {
   std::string wire_file;  // this pair's descriptor under /dev/shm (unlinked on Disconnect)
   bool in_poller = false;
   int peer_pid = 0;  // nvlink wire: the process that owns the peer; probed every 500 ms by get_status
+  std::atomic<bool> peer_dead{false};  // ... and found gone (kept on the host: the mirror is re-published from the device)
   std::chrono::steady_clock::time_point last_probe{};
   int max_sge = 30;  // captured at Init (what the kernels use for this pair)
   // service: payload bytes Recv has returned since the service started (the device keeps the same count;
@@ -684,6 +685,8 @@ extern "C" void b200_pair_init(b200_pair* p) {
   p->max_sge = r.cfg.max_sge;
   p->svc_delivered = 0;
   p->retire_pending = false;
+  p->peer_dead = false;
+  p->peer_pid = 0;
   memset(p->mirror, 0, sizeof(PairMirror));
   bool ok = CU_OK(cudaMemsetAsync(p->ring, 0, cap, r.stream)) &&  // RingBufferPollable::Init
             CU_OK(cudaMemcpyAsync(&r.d_pairs[p->slot], &hd, sizeof(hd), cudaMemcpyHostToDevice, r.stream)) &&
@@ -938,9 +941,10 @@ extern "C" enum b200_status b200_pair_status(b200_pair* p) {
     const auto now = std::chrono::steady_clock::now();
     if (now - p->last_probe > std::chrono::milliseconds(500)) {
       p->last_probe = now;
-      if (kill((pid_t)p->peer_pid, 0) != 0 && errno == ESRCH) ((volatile PairMirror*)p->mirror)->peer_exit = 1;
+      if (kill((pid_t)p->peer_pid, 0) != 0 && errno == ESRCH) p->peer_dead = true;
     }
   }
+  if (p->peer_dead.load() && p->status == B200_CONNECTED) return B200_HALF_CLOSED;
   refresh_remote(p);
   if (p->status == B200_CONNECTED && ((volatile PairMirror*)p->mirror)->peer_exit == 1)
     return B200_HALF_CLOSED;  // pair.cc:354-356
@@ -1450,6 +1454,7 @@ static bool send_is_a_no_op(const b200_pair* p) {
 extern "C" uint64_t b200_pair_send(b200_pair* p, const b200_slice* slices, size_t n, size_t byte_idx) {
   if (!p || !ensure_init()) return 0;
   Runtime& r = R();
+  if (p->peer_dead.load()) return 0;  // nobody owns the remote ring any more: get_status reports HalfClosed
   if (p->status == B200_CONNECTED && n) {
     if (p->peer_local) drain_retire(p->peer_local);  // its Retire may be about to return credit
     refresh_remote(p);
