@@ -460,7 +460,9 @@ def main():
             nvlink = {"error": repr(exc)}
 
     unary = None
-    if rank == 0 and not args.no_unary:
+    if world > 1 and not args.no_unary:
+        unary = {"note": "the unary leg runs in the N=1 line only (it is a one-GPU measurement; the other ranks would idle)"}
+    if rank == 0 and world == 1 and not args.no_unary:
         for b in (bs, bs2, br):
             b.destroy()
         try:
