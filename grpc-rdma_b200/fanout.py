@@ -94,3 +94,89 @@ class RequestFanout:
                 out.append((src, stream, pay_in[pi:pi + n]))
                 pi += n
         return out
+
+
+class InboxFanout:
+    """The data-plane alternative of SURVEY section 8(e): instead of NCCL, a request deframed on GPU a for a stream
+    owned by GPU b travels through an INBOX connection a -> b on the CUDA-IPC / NVLink wire -- the same ring-buffer
+    frames, written by k_send straight into a ring in b's HBM and deframed there by k_recv (credit flows back over
+    NVLink), i.e. through pairs of the C ABI (include/b200_pair.h): nothing but the bootstrap (48-byte address blobs,
+    here over torch.distributed's object collectives) involves the host plumbing of RequestFanout.
+
+    One inbox per ordered (source, destination) pair of ranks.  `exchange` is collective; per epoch each source sends,
+    per destination, one block of (stream id, length) records followed by the payloads; the byte counts are
+    exchanged first so that every rank knows what its inboxes will hold."""
+
+    def __init__(self, pkg, device, group=None):
+        self.pkg, self.group, self.dev = pkg, group, torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.tx = {r: pkg.Pair("inbox-%d-to-%d" % (self.rank, r)) for r in range(self.world) if r != self.rank}
+        self.rx = {r: pkg.Pair("inbox-%d-from-%d" % (self.rank, r)) for r in range(self.world) if r != self.rank}
+        mine = {"tx": {r: p.address() for r, p in self.tx.items()}, "rx": {r: p.address() for r, p in self.rx.items()}}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        for r in self.tx:
+            if not self.tx[r].connect(everyone[r]["rx"][self.rank]) or not self.rx[r].connect(everyone[r]["tx"][self.rank]):
+                raise RuntimeError("inbox connect failed: %s / %s" % (self.tx[r].error(), self.rx[r].error()))
+        dist.barrier(group=group)
+
+    def exchange(self, requests: Sequence[Tuple[int, int, torch.Tensor]]) -> List[Tuple[int, int, torch.Tensor]]:
+        """Same contract as RequestFanout.exchange."""
+        pkg, W, me = self.pkg, self.world, self.rank
+        by_dst = [[] for _ in range(W)]
+        for owner, stream, payload in requests:
+            by_dst[owner].append((stream, payload.reshape(-1)))
+        keep, sops, totals = [], [], {}
+        for dst in range(W):
+            if dst == me or not by_dst[dst]:
+                continue
+            meta = torch.tensor([x for s, p in by_dst[dst] for x in (s, int(p.numel()))], dtype=torch.int64,
+                                device=self.dev).view(torch.uint8)
+            sl = [(meta.data_ptr(), meta.numel())] + [(p.data_ptr(), p.numel()) for _, p in by_dst[dst] if p.numel()]
+            arr = pkg.make_slices(sl)
+            keep += [meta, arr]
+            sops.append((self.tx[dst], arr, len(sl), 0))
+            totals[dst] = sum(n for _, n in sl)
+        counts = [None] * W
+        dist.all_gather_object(counts, {d: (len(by_dst[d]), totals.get(d, 0)) for d in range(W)}, group=self.group)
+        if sops:
+            bs = pkg.Batch("send", sops, pkg.UNTIL_BLOCKED)
+            bs.launch(None)
+            got = bs.results(None)
+            bs.destroy()
+            if got != [totals[d] for d in sorted(totals)]:
+                raise RuntimeError("inbox full: an epoch must fit half the inbox ring -- credit comes back in C/2 steps "
+                                   "(%s of %s accepted)" % (got, totals))
+        dist.barrier(group=self.group)  # the frames have landed in the destinations' rings
+        rops, bufs = [], {}
+        for src in range(W):
+            if src == me:
+                continue
+            nreq, nbytes = counts[src].get(me, (0, 0))
+            if nbytes:
+                bufs[src] = (nreq, torch.empty(nbytes, dtype=torch.uint8, device=self.dev))
+                rops.append((self.rx[src], bufs[src][1].data_ptr(), nbytes))
+        if rops:
+            br = pkg.Batch("recv", rops, pkg.UNTIL_BLOCKED)
+            br.launch(None)
+            got = br.results(None)
+            br.destroy()
+            if got != [bufs[s][1].numel() for s in sorted(bufs)]:
+                raise RuntimeError("inbox delivered %s, expected %s" % (got, [bufs[s][1].numel() for s in sorted(bufs)]))
+        res = []
+        for src in range(W):
+            if src == me:
+                res += [(me, s, p) for s, p in by_dst[me]]
+            elif src in bufs:
+                nreq, buf = bufs[src]
+                meta = buf[:16 * nreq].view(torch.int64).tolist()
+                pos = 16 * nreq
+                for k in range(nreq):
+                    s, n = meta[2 * k], meta[2 * k + 1]
+                    res.append((src, s, buf[pos:pos + n]))
+                    pos += n
+        return res
+
+    def close(self):
+        for p in list(self.tx.values()) + list(self.rx.values()):
+            p.disconnect()
