@@ -23,6 +23,13 @@ PP = C.CDLL(os.path.join(os.path.dirname(pkg.LIB_PATH), "libb200_pingpong.so"))
 PP.b200_pp_run.restype = C.c_double
 PP.b200_pp_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint64)]
 workers = int(os.environ.get("SVC_WORKERS", "32"))
+try:
+    MAXG = max(1, len(os.sched_getaffinity(0)) // 2)
+    q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+    if q != "max":
+        MAXG = max(1, min(MAXG, int(int(q) / int(per)) // 2))
+except Exception:
+    MAXG = 8
 
 
 def pct(r):
@@ -31,6 +38,7 @@ def pct(r):
 
 
 def pingpong(conns, groups, iters, m=1024):
+    groups = min(groups, MAXG)          # client + server threads never exceed the cores of the box
     rtt = np.zeros(conns * iters, dtype=np.uint64)
     t = PP.b200_pp_run(conns, groups, iters, max(5, iters // 10), m, rtt.ctypes.data_as(C.POINTER(C.c_uint64)))
     d = pct(rtt) if t > 0 else {"error": int(t)}
