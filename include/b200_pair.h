@@ -190,6 +190,8 @@ int b200_poller_scan(b200_pair* const* pairs, size_t n, uint32_t* events);
  * persistent kernel is resident: the library defers its own frees until b200_service_stop, and
  * callers must use stream-level waits.
  */
+/* `workers` = pool CTAs (B200_SERVICE_WORKERS, default 16); B200_SERVICE_OWNERS = owner warps = host command queues
+ * (default 32).  Fails (-1) when the resident grids would not fit on the device together. */
 int b200_service_start(int workers);
 /* Call with no b200_pair_send / recv in flight (they would wait for a worker that has left). */
 void b200_service_stop(void);
@@ -235,6 +237,10 @@ uint64_t b200_service_eager_hits(void);
  *                        write the pinned buffers directly (GPUDirect-style, no staging).
  */
 
+/* Threading of this section: a prepared batch belongs to one thread at a time (launch / results / destroy are not
+ * locked against each other); different batches may be driven from different threads, the host-staged lanes and the
+ * runtime's default stream are shared, so concurrent launches interleave there in submission order.
+ * b200_pairs_submit and the post / poll calls are thread-safe (per-queue posting sections, per-thread staging). */
 typedef struct b200_send_op {
   b200_pair* pair;
   const b200_slice* slices; /* host array of n entries (copied at submit) */

@@ -61,3 +61,34 @@ def test_against_oracle_and_reference(dev, oracle):
                 assert dev.dev_free_size(cap, h, t) == ref.L.ref_free_size(ring, h, t)
     if ring:
         ref.L.ref_ring_destroy(ring)
+
+
+def test_service_wire_structs_and_eager_checksum():
+    """Layout of what crosses PCIe between the host and the resident service warps, and the eager-push checksum:
+    order-independent over lanes (the warp XOR-reduces lane-strided partial sums, the host walks the words),
+    sensitive to every byte, to the size and to the delivered-count it was pushed for."""
+    import ctypes as C
+    import numpy as np
+    subprocess.check_call(["make", "-s", "-C", endpoint_lib.NATIVE, "libdev_helpers.so"])
+    D = C.CDLL(os.path.join(endpoint_lib.NATIVE, "libdev_helpers.so"))
+    for f in ("dev_sizeof_svcdone", "dev_sizeof_eagerrec", "dev_offset_stamp2"):
+        getattr(D, f).restype = C.c_uint64
+    assert D.dev_sizeof_svcdone() == 16          # one 16-byte store: bytes, calls and stamp become visible together
+    assert D.dev_sizeof_eagerrec() == 32
+    assert D.dev_offset_stamp2() == 124          # second stamp in the second 64-byte half of the command line
+    D.dev_eager_checksum.restype = C.c_uint64
+    D.dev_eager_checksum.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int]
+    rng = np.random.default_rng(5)
+    for size in (1, 7, 8, 9, 255, 1024, 2047, 2048):
+        buf = rng.integers(0, 256, size + 8, dtype=np.uint8)
+        ref = D.dev_eager_checksum(buf.ctypes.data, size, 12345, 1)
+        assert D.dev_eager_checksum(buf.ctypes.data, size, 12345, 32) == ref      # warp form == host form
+        assert D.dev_eager_checksum(buf.ctypes.data, size, 12346, 1) != ref       # another delivered count
+        if size > 1:
+            assert D.dev_eager_checksum(buf.ctypes.data, size - 1, 12345, 1) != ref
+        b2 = buf.copy()
+        b2[size - 1] ^= 1
+        assert D.dev_eager_checksum(b2.ctypes.data, size, 12345, 1) != ref         # last byte counts
+        b3 = buf.copy()
+        b3[size] ^= 0xFF
+        assert D.dev_eager_checksum(b3.ctypes.data, size, 12345, 1) == ref         # bytes past the frame do not
