@@ -39,3 +39,10 @@ g++ -std=c++14 -O2 -w -include cstdint $EXINC -o $OUT/test_echo_cs_b200 $ROOT/in
 # the in-process fake verbs + the mini HdrHistogram are still linked (RDMA_EVENT mode objects reference them): ship them beside the binary
 cp $PFX/lib/libibverbs.so $PFX/lib/libhdr_histogram.so $OUT/
 echo "built $OUT/test_echo_cs_b200"; ls -la $OUT
+# the reference's micro-benchmark driver over the same swapped core (two processes: they meet on the CUDA-IPC wire)
+MB="$EX/gen/micro_benchmark.pb.o $EX/gen/micro_benchmark.grpc.pb.o"
+MBINC="$EXINC -I$ROOT/integration/stack/shim_mb -I$REF/examples/cpp/micro-bench"
+g++ -std=c++14 -O2 -w -include cstdint -DGRPC_USE_IBVERBS $MBINC -o $OUT/mb_server_b200 $REF/examples/cpp/micro-bench/mb_server.cc $MB $LIBS
+g++ -std=c++14 -O2 -w -include cstdint -DGRPC_USE_IBVERBS $MBINC -o $OUT/mb_client_b200 $REF/examples/cpp/micro-bench/mb_client.cc $MB $LIBS
+strip $OUT/test_echo_cs_b200 $OUT/mb_server_b200 $OUT/mb_client_b200
+ls -la $OUT

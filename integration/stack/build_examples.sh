@@ -31,3 +31,13 @@ build hw_greeter_client $REF/examples/cpp/helloworld/greeter_client.cc $HW
 g++ $CXXFLAGS $INC -Dmain=server_main -c $REF/examples/cpp/test/greeter_server.cc -o $EX/gen/test_server.o
 g++ $CXXFLAGS $INC -Dmain=client_main -c $REF/examples/cpp/test/greeter_client.cc -o $EX/gen/test_client.o
 build test_echo_cs $ROOT/integration/stack/cs_main.cc $EX/gen/test_server.o $EX/gen/test_client.o $HW
+# the reference's micro-benchmark driver (examples/cpp/micro-bench: the workload of BASELINE configs[1..4]); MPI and
+# libnuma are not in the image: single-rank / no-NUMA stand-ins under integration/stack/shim_mb
+(cd $B && ninja -j6 absl_flags absl_flags_parse absl_flags_usage absl_flags_usage_internal absl_flags_reflection absl_flags_marshalling \
+   absl_flags_internal absl_flags_config absl_flags_program_name absl_flags_commandlineflag absl_flags_commandlineflag_internal \
+   absl_flags_private_handle_accessor > /dev/null)
+LIBS="-Wl,--start-group $(find $B -name '*.a' | grep -v -e libprotoc -e plugin_support | tr '\n' ' ') -Wl,--end-group \
+  -L$PFX/lib -libverbs -lhdr_histogram -Wl,-rpath,$PFX/lib -lssl -lcrypto -lz -lpthread -ldl -lrt"
+MB="$EX/gen/micro_benchmark.pb.o $EX/gen/micro_benchmark.grpc.pb.o"
+EXTRA="-I$ROOT/integration/stack/shim_mb" build mb_server $REF/examples/cpp/micro-bench/mb_server.cc $MB
+EXTRA="-I$ROOT/integration/stack/shim_mb -I$REF/examples/cpp/micro-bench" build mb_client $REF/examples/cpp/micro-bench/mb_client.cc $MB

@@ -21,3 +21,10 @@ for MODE in TCP RDMA_BPEV; do
   T1=$(date +%s.%N)
   echo "examples/cpp/test echo $MODE: rc=$RC, $(grep -c 'received\.' echo_$MODE.log) replies equal to their request, mode lines: $(grep -o 'Select [A-Za-z ]* mode' echo_$MODE.log | sort | uniq -c | tr '\n' ';'), $(python3 -c "print(round($T1 - $T0, 1))") s"
 done
+# the reference's micro-benchmark driver (unary, 1 KiB requests) over TCP: server and client as two processes
+GRPC_PLATFORM_TYPE=TCP timeout 40 ./mb_server --port=50079 --threads=2 --cqs=2 --resp=8 > mb_srv.log 2>&1 &
+SP=$!
+sleep 1.5
+GRPC_PLATFORM_TYPE=TCP timeout 20 stdbuf -oL ./mb_client --target=localhost:50079 --req=1024 --concurrent=1 --duration=3 --warmup=100 > mb_cli.log 2>&1
+echo "micro-bench TCP (mb_server + mb_client): rc=$?, $(grep Aggregated mb_cli.log), $(tail -1 mb_cli.log)"
+kill $SP 2>/dev/null; wait $SP 2>/dev/null
