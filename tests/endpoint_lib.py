@@ -36,5 +36,7 @@ def load(pkg, need_oracle):
         O = C.CDLL(os.path.join(NATIVE, "liboracle_pair_ops.so"))
         O.oracle_pair_ops.restype = C.c_void_p
         O.oracle_ops_config.argtypes = [u64, C.c_int]
+        O.oracle_pair_ops_batch.restype = C.c_void_p
+        O.oracle_pair_ops_async.restype = C.c_void_p
         ops = (O, O.oracle_pair_ops())
     return D, ops

@@ -98,3 +98,50 @@ static const b200_pair_ops kOps = {o_take,   o_putback, o_init,    o_addr,     o
                                    o_wfd,    o_consume, o_disconnect, o_noop,  o_noop};
 
 const b200_pair_ops* oracle_pair_ops(void) { return &kOps; }
+
+/* ---- the B200-native widening of the table, over the same oracle: `submit` (one pass = the rdma_flush loops and
+ * rdma_do_read loops of every queued endpoint, oracle's orb_pair_send_all / orb_pair_recv_drain) and the
+ * completion-queue form (an op finishes at post time; poll just hands the count back).  With these the engine's
+ * batching and pump code paths run on the CPU. */
+static int o_submit(const b200_send_op* s, size_t ns, uint64_t* acc, const b200_recv_op* r, size_t nr, uint64_t* del,
+                    int flags) {
+  for (size_t i = 0; i < ns; i++) {
+    orb_pair* p = ((opair*)s[i].pair)->p;
+    acc[i] = (flags & B200_BATCH_UNTIL_BLOCKED) ? orb_pair_send_all(p, (const orb_slice*)s[i].slices, s[i].nslices, s[i].byte_idx, NULL)
+                                                : orb_pair_send(p, (const orb_slice*)s[i].slices, s[i].nslices, s[i].byte_idx);
+  }
+  for (size_t i = 0; i < nr; i++) {
+    orb_pair* p = ((opair*)r[i].pair)->p;
+    del[i] = (flags & B200_BATCH_UNTIL_BLOCKED) ? orb_pair_recv_drain(p, r[i].dst, r[i].cap, NULL) : orb_pair_recv(p, r[i].dst, r[i].cap);
+  }
+  return 0;
+}
+static void* o_post_send(void* v, const b200_slice* s, size_t n, size_t b, int flags, int* again) {
+  uint64_t* h = (uint64_t*)malloc(sizeof(uint64_t));
+  orb_pair* p = ((opair*)v)->p;
+  *again = 0;
+  *h = (flags & B200_BATCH_UNTIL_BLOCKED) ? orb_pair_send_all(p, (const orb_slice*)s, n, b, NULL) : orb_pair_send(p, (const orb_slice*)s, n, b);
+  return h;
+}
+static void* o_post_recv(void* v, void* dst, uint64_t cap, int flags, int* again) {
+  uint64_t* h = (uint64_t*)malloc(sizeof(uint64_t));
+  orb_pair* p = ((opair*)v)->p;
+  *again = 0;
+  *h = (flags & B200_BATCH_UNTIL_BLOCKED) ? orb_pair_recv_drain(p, dst, cap, NULL) : orb_pair_recv(p, dst, cap);
+  return h;
+}
+static int o_poll(void* op, uint64_t* bytes) {
+  *bytes = *(uint64_t*)op;
+  free(op);
+  return 1;
+}
+static const b200_pair_ops kOpsBatch = {o_take,   o_putback, o_init,    o_addr,     o_connect, o_send,
+                                        o_recv,   o_has_msg, o_pending, o_readable, o_status,  o_error,
+                                        o_wfd,    o_consume, o_disconnect, o_noop,  o_noop,    o_submit,
+                                        NULL,     NULL,      NULL,      NULL,       NULL};
+static const b200_pair_ops kOpsAsync = {o_take,   o_putback, o_init,    o_addr,     o_connect, o_send,
+                                        o_recv,   o_has_msg, o_pending, o_readable, o_status,  o_error,
+                                        o_wfd,    o_consume, o_disconnect, o_noop,  o_noop,    o_submit,
+                                        NULL,     NULL,      o_post_send, o_post_recv, o_poll};
+const b200_pair_ops* oracle_pair_ops_batch(void) { return &kOpsBatch; }
+const b200_pair_ops* oracle_pair_ops_async(void) { return &kOpsAsync; }

@@ -107,3 +107,31 @@ def test_engine_lock_is_not_held_across_the_wait(drv):
     worst = C.c_uint64(0)
     assert D.drv_two_threads(ops, 200, 5, C.byref(worst)) == 0
     assert worst.value < 50_000, "a call blocked for %d us behind the sleeping engine" % worst.value
+
+
+@pytest.mark.parametrize("mode", ["batch", "async"])
+def test_batching_engine_host_logic(drv, mode, monkeypatch):
+    """The engine's batching paths on the CPU: an ops table WITH `submit` (one b200_pairs_submit-shaped call per
+    pass: the rdma_flush / rdma_do_read loops of every queued endpoint) and one with the completion-queue form
+    (post / poll, B200_ENDPOINT_ASYNC=1) over the oracle -- conformance shapes, a ring smaller than a write (partial
+    writes re-armed through has_pending_writes), shutdown, peer close, echo and 120 connections on one engine."""
+    D, O, _ = drv
+    ops = O.oracle_pair_ops_batch() if mode == "batch" else O.oracle_pair_ops_async()
+    if mode == "async":
+        monkeypatch.setenv("B200_ENDPOINT_ASYNC", "1")
+    O.oracle_ops_config(65536, 30)
+    assert D.drv_read_and_write(ops, 2_000_000, 100_000, 8192, 0, 50, 0, None) == 0
+    assert D.drv_read_and_write(ops, 60_000, 10_000, 1, 0, 50, 0, None) == 0
+    assert D.drv_read_and_write(ops, 10_000_000, 100_000, 1, 1, 50, 0, None) == 0       # with shutdown
+    O.oracle_ops_config(1024, 30)
+    for i in (1, 7, 64, 513, 999):
+        assert D.drv_read_and_write(ops, 40320, i, i, 0, 50, 0, None) == 0, i
+    O.oracle_ops_config(4096, 30)
+    assert D.drv_read_and_write(ops, 300_000, 300_000, 100_000, 0, 50, 0, None) == 0    # message > ring and staging
+    assert D.drv_shutdown_sequence(ops, 50) == 0
+    assert D.drv_peer_close(ops, 50, 0) == 0
+    O.oracle_ops_config(65536, 30)
+    nbytes = C.c_uint64(0)
+    assert D.drv_echo(ops, 40, 300_000, 12345, 50, 0, 0, C.byref(nbytes)) == 0 and nbytes.value > 0
+    O.oracle_ops_config(16384, 30)
+    assert D.drv_multi_echo(ops, 120, 3, 20_000, 99, 50, 0, 0, None) == 0
