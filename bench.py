@@ -189,6 +189,15 @@ def run_cpu_baseline(args, lens, payload_per_msg, seconds):
                       % (conns, msgs, payload_per_msg, args.ring_kb, t, threads, cores)}
 
 
+def bench_config(conns, msg_bytes, ring_kb):
+    """The workload both arms are timed on, spelled identically in both JSON lines (BASELINE configs[1])."""
+    return {"workload": "configs[1]: streaming, %d connections per GPU x %d-byte chttp2-shaped messages, ring %d KiB"
+                        % (conns, msg_bytes, ring_kb),
+            "connections": conns, "message_bytes": msg_bytes, "ring_kb": ring_kb,
+            "l2": "inputs larger than the cache (every step streams %.2f GiB of slices through %.1f GiB of rings, "
+                  "no reuse between steps)" % (conns * (msg_bytes + 4626) / 2**30, conns * ring_kb / 2**20)}
+
+
 def reference_arm(args):
     """--impl reference: the reference's own CPU path (oracle/_ref when built, else the port)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -215,9 +224,9 @@ def reference_arm(args):
         "ms_per_step": t_total / steps_done * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "msgs_per_s": n_total / t_total,
-        "config": {"workload": "streaming 4 MiB chttp2-shaped messages, %d connections, ring %d KiB; "
-                               "reference CPU RDMA_BPEV path (PairPollable::Send/Recv, memcpy wire)"
-                               % (conns, args.ring_kb), "connections": conns, "message_bytes": args.msg_bytes},
+        "config": bench_config(conns, args.msg_bytes, args.ring_kb),
+        "config_details": {"arm": "reference CPU RDMA_BPEV path (PairPollable::Send/Recv, memcpy wire)",
+                           "connections_timed": conns},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": kind,
                          "sample": "each step = 1 msg on each of %d conns; %d timed steps, %d threads of %d cores" % (conns, steps_done, threads, cores)},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -490,11 +499,10 @@ def main():
             "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": t_dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "msgs_per_s": n_msgs / (t_dev_ms * 1e-3),
-            "config": {"workload": "configs[1]: streaming, 4 MiB chttp2-shaped messages (514 slices: 9 B DATA "
-                                   "headers + <=16384 B payload), %d connections per GPU, HBM ring %d KiB, loopback "
-                                   "wire (sender writes the peer ring in HBM), 1 message per connection per step"
-                                   % (conns, args.ring_kb),
-                       "connections_per_gpu": conns, "message_bytes": msg, "ring_kb": args.ring_kb,
+            "config": bench_config(conns, msg, args.ring_kb),
+            "config_details": {"arm": "B200: HBM rings, loopback wire (sender writes the peer ring in HBM), 1 message per "
+                                      "connection per step; 514 slices per message: 9 B DATA headers + <=16384 B payload",
+                               "connections_per_gpu": conns, "connections_total": conns * world,
                        "l2": "inputs larger than L2: %.2f GiB of slices + %.1f GiB of rings per GPU, no reuse "
                              "between steps" % (conns * total / 2**30, conns * args.ring_kb / 2**20),
                        "sharding": "connection c of rank r is independent; no data-path collective",
