@@ -176,26 +176,28 @@ int b200_poller_scan(b200_pair* const* pairs, size_t n, uint32_t* events);
 
 /* ----------------------------------------------------------------- service */
 /*
- * The persistent kernel of the unary path (the "persistent warp-per-connection kernel" and the
- * busy-poll half of the BPEV completion loop).  b200_service_start(workers) launches ONE resident
- * kernel: `workers` CTAs that execute Send / Recv commands the host posts into pinned mapped
- * memory -- the same device code as the one-shot kernels, but no launch and no stream
- * synchronisation per call -- plus one poller CTA that scans the connection table continuously,
- * keeps every pair's host-visible mirror current (so HasMessage / HasPendingWrites / get_status
- * stay wait-free host reads without any scan launch) and appends readiness CHANGES to a ready
- * ring in mapped host memory with one atomic per warp.  While it runs, b200_pair_send / recv go
- * through it and the background Poller threads consume the ready ring instead of launching
- * scans.  workers <= 0: B200_SERVICE_WORKERS (16).  Returns 0 / -1.
- * Device-wide synchronisation (cudaDeviceSynchronize, cudaFree) never completes while a
- * persistent kernel is resident: the library defers its own frees until b200_service_stop, and
- * callers must use stream-level waits.
+ * The resident kernels of the unary path (the "persistent warp-per-connection kernel" and the busy-poll half of the
+ * BPEV completion loop).  b200_service_start launches three of them and keeps them resident:
+ *   owners  one WARP per host command queue.  b200_pair_send / recv post a 128-byte command into the queue of the
+ *           pair's connection (both ends of a loopback connection share a queue) and spin on a 16-byte answer.  A
+ *           small call (a unary message) is planned, moved, retired and published by that warp alone -- no launch,
+ *           no stream synchronisation, no CTA barrier, no lock; a frame that lands at the head of the peer's ring
+ *           is pushed to the peer's host slot at once, so the peer's Recv does not need a trip to the GPU.
+ *   pool    `workers` CTAs with the k_send / k_recv machinery for everything larger (and for the rdma_flush /
+ *           rdma_do_read loops of b200_pairs_submit), fed by the owners through mailboxes in device memory.
+ *   poller  scans the connection table continuously, keeps the host-visible mirror of pairs on the nvlink wire
+ *           current and appends readiness CHANGES to a ready ring in mapped host memory (one atomic per warp); the
+ *           background Poller threads turn those into eventfd kicks instead of launching scans.
+ * Returns 0 / -1.  While the service runs: no device-wide synchronisation (cudaDeviceSynchronize, cudaFree; the
+ * library defers its own frees until b200_service_stop) and no FIRST launch of a kernel in the process (lazy module
+ * loading waits for an idle device; the library loads all of its own kernels before it starts the service).
  */
 /* `workers` = pool CTAs (B200_SERVICE_WORKERS, default 16); B200_SERVICE_OWNERS = owner warps = host command queues
  * (default 32).  Fails (-1) when the resident grids would not fit on the device together. */
 int b200_service_start(int workers);
 /* Call with no b200_pair_send / recv in flight (they would wait for a worker that has left). */
 void b200_service_stop(void);
-int b200_service_running(void); /* number of worker CTAs, 0 = not running */
+int b200_service_running(void); /* number of pool CTAs, 0 = not running */
 /* out[0] commands executed, [1] ready-ring entries consumed, [2] ready-ring overruns,
  * [3] device poller scans (updated every 1024 scans) */
 void b200_service_stats(uint64_t out[4]);
